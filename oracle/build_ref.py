@@ -1,0 +1,127 @@
+#!/usr/bin/env python3
+"""oracle/build_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Builds the *unmodified algorithm* of the miniVite reference (sources read where
+they lie under /root/reference) into ``oracle/_ref/miniVite_ref`` using the
+``oracle/mpi_shim/mpi.h`` stand-in for MPI.  Nothing from the reference is
+copied into the repository: the sources are patched in a throw-away temp
+directory (only *observation* hooks are injected, all gated by environment
+variables, so an un-instrumented run executes exactly the reference's code)
+and only the resulting binary lands in ``oracle/_ref/`` (git-ignored, but it
+travels to the GPU box with the gpurun snapshot).
+
+Hooks (all on stderr / side files, all off unless the env var is set):
+  MV_TRACE=1          per iteration: ``ITER k mod=%.17g moved=N chash=HEX`` and at
+                      the end ``FINAL prevMod=.. chashCurr=.. constant=.. ncomm=.. nprocs=..``
+                      (dspl.hpp:1400 / dspl.hpp:1430; shard-combinable hash of SURVEY 8(c))
+  MV_DUMP_COMM=pfx    rank r writes ``pfx.r``: int64 base, int64 nv, int64 currComm[nv]
+  MV_DUMP_GRAPH=pfx   rank r writes ``pfx.r``: int64 base, lnv, lne, rowptr[lnv+1], Edge[lne]
+                      right after graph creation (main.cpp:123)
+  always              rank 0 prints ``RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d``
+                      to stderr next to the reference's own report block (main.cpp:178)
+
+Usage: python oracle/build_ref.py [--ref /root/reference] [--force]
+"""
+import argparse
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(HERE, "_ref")
+SHIM_DIR = os.path.join(HERE, "mpi_shim")
+
+HASH_FN = r"""
+static inline unsigned long long mv_mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31);
+}
+static inline unsigned long long mv_vhash(long long gid, long long val) {
+  return mv_mix64(((unsigned long long)gid) * 0x9E3779B97F4A7C15ULL ^ (unsigned long long)val);
+}
+"""
+
+HOOK_ITER = r"""    if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; GraphElem mv = 0, mvg = 0;
+      for (GraphElem i = 0; i < nv; i++) { hl += mv_vhash(i + base, targetComm[i]); mv += (targetComm[i] != currComm[i]); }
+      MPI_Allreduce(&hl, &hg, 1, MPI_INT64_T, MPI_SUM, gcomm); MPI_Allreduce(&mv, &mvg, 1, MPI_INT64_T, MPI_SUM, gcomm);
+      if (me == 0) fprintf(stderr, "ITER %d mod=%.17g moved=%ld chash=%016llx\n", numIters, currMod, (long)mvg, hg); }
+"""
+
+HOOK_FINAL = r"""  iters = numIters;
+  if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; GraphElem nc = 0, ncg = 0;
+    for (GraphElem i = 0; i < nv; i++) { hl += mv_vhash(i + base, currComm[i]); }
+    for (GraphElem i = 0; i < nv; i++) { nc += (localCinfo[i].size > 0); }
+    MPI_Allreduce(&hl, &hg, 1, MPI_INT64_T, MPI_SUM, gcomm); MPI_Allreduce(&nc, &ncg, 1, MPI_INT64_T, MPI_SUM, gcomm);
+    if (me == 0) fprintf(stderr, "FINAL prevMod=%.17g chashCurr=%016llx constant=%.17g ncomm_after_last=%ld nprocs=%d\n",
+                         prevMod, hg, constantForSecondTerm, (long)ncg, nprocs); }
+  if (getenv("MV_DUMP_COMM")) { char fn[4096]; snprintf(fn, sizeof fn, "%s.%d", getenv("MV_DUMP_COMM"), me);
+    FILE *f = fopen(fn, "wb"); long long hdr[2] = {(long long)base, (long long)nv};
+    fwrite(hdr, 8, 2, f); fwrite(currComm.data(), sizeof(GraphElem), nv, f); fclose(f); }
+"""
+
+HOOK_GRAPH = r"""  assert(g != nullptr);
+  if (getenv("MV_DUMP_GRAPH")) { char fn[4096]; snprintf(fn, sizeof fn, "%s.%d", getenv("MV_DUMP_GRAPH"), me);
+    FILE *f = fopen(fn, "wb"); long long hdr[3] = {(long long)g->get_base(me), (long long)g->get_lnv(), (long long)g->get_lne()};
+    fwrite(hdr, 8, 3, f); fwrite(g->edge_indices_.data(), sizeof(GraphElem), g->get_lnv() + 1, f);
+    fwrite(g->edge_list_.data(), sizeof(Edge), g->get_lne(), f); fclose(f); }
+"""
+
+HOOK_RESULT = r"""      double avgt = (tot_time / nprocs);
+      fprintf(stderr, "RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d threads=%d\n", currMod, iters, avgt,
+              (long)g->get_nv(), (long)g->get_ne(), nprocs, omp_get_max_threads());
+"""
+
+
+def replace_once(text, old, new, what):
+    if text.count(old) != 1:
+        raise SystemExit(f"build_ref: anchor for {what!r} found {text.count(old)} times (expected 1)")
+    return text.replace(old, new, 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--force", action="store_true")
+    args = ap.parse_args()
+    out_bin = os.path.join(OUT_DIR, "miniVite_ref")
+    if not os.path.isdir(args.ref):
+        if os.path.exists(out_bin):
+            print(f"build_ref: {args.ref} absent; keeping prebuilt {out_bin}")
+            return 0
+        print(f"build_ref: {args.ref} absent and no prebuilt binary", file=sys.stderr)
+        return 1
+    srcs = [os.path.join(args.ref, f) for f in ("main.cpp", "dspl.hpp", "graph.hpp", "utils.hpp")]
+    stamp = max(os.path.getmtime(p) for p in srcs + [__file__, os.path.join(SHIM_DIR, "mpi.h")])
+    if not args.force and os.path.exists(out_bin) and os.path.getmtime(out_bin) >= stamp:
+        print(f"build_ref: {out_bin} up to date")
+        return 0
+    os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="mvref_")
+    try:
+        for p in srcs:
+            shutil.copy(p, tmp)
+        d = open(os.path.join(tmp, "dspl.hpp")).read()
+        d = replace_once(d, "static MPI_Datatype commType;\n", "static MPI_Datatype commType;\n" + HASH_FN, "hash fn")
+        d = replace_once(d, "    // exit criteria\n    if (currMod - prevMod < thresh)",
+                         HOOK_ITER + "    // exit criteria\n    if (currMod - prevMod < thresh)", "iteration hook")
+        d = replace_once(d, "  iters = numIters;\n", HOOK_FINAL, "final hook")
+        open(os.path.join(tmp, "dspl.hpp"), "w").write(d)
+        m = open(os.path.join(tmp, "main.cpp")).read()
+        m = replace_once(m, "  assert(g != nullptr);\n", HOOK_GRAPH, "graph dump hook")
+        m = replace_once(m, "      double avgt = (tot_time / nprocs);\n", HOOK_RESULT, "result hook")
+        open(os.path.join(tmp, "main.cpp"), "w").write(m)
+        # The reference Makefile builds with -O3 -fopenmp -DPRINT_DIST_STATS (Makefile:10-16);
+        # -std=c++11 implies -ffp-contract=off on x86-64 and no -march flag means no FMA.
+        cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-DPRINT_DIST_STATS",
+               "-I", SHIM_DIR, "-I", tmp, os.path.join(tmp, "main.cpp"), "-o", out_bin]
+        print("build_ref:", " ".join(cmd))
+        subprocess.check_call(cmd)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    print(f"build_ref: wrote {out_bin}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
