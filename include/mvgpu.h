@@ -1,0 +1,113 @@
+/* mvgpu.h -- C ABI of the B200-native Louvain phase (drop-in for miniVite's distLouvainMethod).
+ *
+ * The reference has no FFI; its seam is one C++ call, main.cpp:168-169:
+ *
+ *     currMod = distLouvainMethod(me, nprocs, *g, ssz, rsz, ssizes, rsizes, svdata, rvdata,
+ *                                 currMod, threshold, iters);            // dspl.hpp:1280-1283
+ *
+ * whose inputs are the arrays of `class Graph` (graph.hpp:85-296): `edge_indices_` (int64 local
+ * offsets, lnv+1 entries), `edge_list_` ({int64 tail_; double weight_} = 16 B records with GLOBAL
+ * tails), the partition `parts_` (nprocs+1 entries) and the scalars nv / lnv / lne.  The entry points
+ * below take exactly those plain arrays -- no C++ or torch types cross the boundary -- and return
+ * what the reference returns (modularity of the last accepted iteration, iteration count) plus the
+ * final assignment, which the reference computes but never exports (dspl.hpp:1432-1438).
+ *
+ * One context == one rank == one GPU.  All functions return 0 on success; on failure they return a
+ * non-zero code and mvgpu_last_error() describes it (no exceptions cross the boundary; the host
+ * wrapper turns a failure into the reference's MPI_Abort(-99) behaviour).  A context must be driven
+ * by one host thread at a time.  The library never falls back to a CPU implementation: without a
+ * usable CUDA device every compute entry point fails.
+ */
+#ifndef MVGPU_H
+#define MVGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvgpu_ctx mvgpu_ctx;
+
+#define MVGPU_UNIQUE_ID_BYTES 128
+
+/* Per-iteration record; mirrors the trace hook injected into the reference at dspl.hpp:1400. */
+typedef struct {
+  double modularity;   /* currMod of the iteration (dspl.hpp:447-448) */
+  int64_t moved;       /* #{i : targetComm[i] != currComm[i]}, all ranks */
+  uint64_t chash;      /* sum over vertices of mix64(gid*0x9E3779B97F4A7C15 ^ targetComm), mod 2^64, all ranks */
+} mvgpu_iter_trace;
+
+/* Device-side timing of the last mvgpu_louvain call (CUDA events on the context's stream). */
+typedef struct {
+  double total_s;        /* the reference's main.cpp:162-173 scope: setup + all iterations */
+  double setup_s;        /* format conversion + ghost discovery (exchangeVertexReqs, dspl.hpp:1106-1272) + init (151-172) */
+  double scan_s;         /* sum over iterations of the neighbour-scan kernel(s) (dspl.hpp:276-405) */
+  double fold_s;         /* sum of fold + modularity partial kernels (dspl.hpp:458-471, 407-456) */
+  double exchange_s;     /* sum of ghost exchange + collectives (dspl.hpp:488-952, 978-1103, 441) */
+  double h2d_s;          /* host->device copy of the shard (mvgpu_upload_shard), not part of total_s */
+  int64_t scan_launches; /* neighbour-scan kernel launches in the call */
+  int64_t kernel_launches; /* all kernels of this library launched inside total_s */
+  int32_t iters;
+  int32_t unit_weight;   /* 1 if the integer fast path ran (all weights 1.0, 2m < 2^31) */
+} mvgpu_timings;
+
+const char *mvgpu_last_error(void);
+/* Number of CUDA devices visible, or -1 (and an error string) when CUDA is unusable. */
+int mvgpu_device_count(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Replaces the rank identity the reference takes from MPI_Comm_rank/size (main.cpp:97-98). */
+int mvgpu_create(mvgpu_ctx **ctx, int device, int rank, int nranks);
+int mvgpu_destroy(mvgpu_ctx *ctx);
+
+/* ---- multi-GPU plumbing (nranks > 1 only) ---------------------------------------------------- */
+/* Rank 0 creates the id and ships the 128 bytes to every rank by any means (torch.distributed
+ * broadcast, a pipe, a file); every rank then calls mvgpu_comm_init.  Stands in for MPI_Init +
+ * createCommunityMPIType (main.cpp:78-102). */
+int mvgpu_get_unique_id(void *id128);
+int mvgpu_comm_init(mvgpu_ctx *ctx, const void *id128);
+
+/* ---- graph hand-off -------------------------------------------------------------------------- */
+/* Host arrays of a reference Graph shard (graph.hpp:289-293): copies them to HBM.
+ * parts: nranks+1 global vertex offsets (graph.hpp:109-113 or the -b bins, graph.hpp:511);
+ * edge_indices: lnv+1 LOCAL offsets; edge_list: lne records {int64 tail; double weight}. */
+int mvgpu_upload_shard(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
+                       const int64_t *edge_indices, const void *edge_list);
+/* Same, for arrays that already live in this context's device memory (not copied, not freed). */
+int mvgpu_attach_shard_device(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
+                              const int64_t *d_edge_indices, const void *d_edge_list);
+
+/* ---- the Louvain phase (dspl.hpp:1280-1441) --------------------------------------------------- */
+/* lower/thresh as in the reference (main.cpp:149,70); *iters counts the rejected last iteration
+ * (dspl.hpp:1430); *modularity is prevMod (dspl.hpp:1440).  Collective over all ranks. */
+int mvgpu_louvain(mvgpu_ctx *ctx, double lower, double thresh, int *iters, double *modularity);
+
+/* currComm of this rank's vertices at exit (global community ids), lnv entries. */
+int mvgpu_get_communities(mvgpu_ctx *ctx, int64_t *out);
+/* Same values left in device memory (int32 global ids); valid until the next mvgpu_louvain. */
+int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
+
+/* Options: "trace" (0/1: record moved/chash per iteration, default 0), "max_iters" (safety cap,
+ * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
+ * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off). */
+int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
+int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);
+int mvgpu_get_timings(mvgpu_ctx *ctx, mvgpu_timings *out);
+/* 1/(2m), the reference's constantForSecondTerm (dspl.hpp:129), of the last run. */
+int mvgpu_get_constant(mvgpu_ctx *ctx, double *out);
+/* Shard statistics after upload/louvain: info[0]=lnv, [1]=lne, [2]=nghost, [3]=send list length,
+ * [4]=#high-degree vertices, [5]=max degree. */
+int mvgpu_get_shard_info(mvgpu_ctx *ctx, int64_t *info6);
+
+/* ---- one-call form of the reference seam ------------------------------------------------------ */
+/* distLouvainMethod(me, nprocs, g, ..., lower, thresh, iters) for a single-GPU run with HOST arrays:
+ * create + upload + louvain (+ optional assignment download into comm_out, may be NULL) + destroy. */
+int mvgpu_dist_louvain_method(int device, int64_t nv, int64_t ne_local, const int64_t *edge_indices,
+                              const void *edge_list, double lower, double thresh, int *iters,
+                              double *modularity, int64_t *comm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVGPU_H */

@@ -1,0 +1,612 @@
+// Device kernels of the Louvain phase for sm_100a (B200).  Hand-written CUDA; no tensor cores: the
+// path is a sparse gather/scan, bound by L2/HBM sector throughput.
+//
+// Data layout in HBM (per rank/GPU; built once per run by the setup kernels from the reference-format
+// arrays int64 rowptr[lnv+1] + {int64 tail; double w}[lne]):
+//   rowptr   uint32[lnv+1]          local edge offsets (lne < 2^32 per shard)
+//   tails    int32[lne]             LOCAL SLOT of the neighbour: [0,lnv) own vertex, [lnv,lnv+nghost) ghost
+//                                   (replaces the reference's per-edge owner test + unordered_map lookup,
+//                                   dspl.hpp:251-260)
+//   weights  double[lne]            only when some weight != 1.0
+//   cur/tgt  int32[lnv+nghost]      community (GLOBAL id) of every slot; ghosts are refreshed by the
+//                                   per-iteration exchange (dspl.hpp:559-688)
+//   unit-weight fast path (all weights 1, 2m < 2^31):
+//     cinfo  uint64[lnv]  = size<<32 | degree   (Comm{size,degree}, dspl.hpp:61-66, both exact integers)
+//     upd    uint64[lnv]  = packed two's-complement delta: ONE 64-bit atomic per community update
+//                           and fold is a single integer add (dspl.hpp:339-346 + 458-471)
+//   weighted path: cinfo_w {int64 size; double degree}[lnv], usize int64[lnv], udeg double[lnv], vdeg double[lnv]
+// With 32-bit ids the gathered arrays at 16M vertices are 64 MB (cur) + 128 MB (cinfo): largely L2 resident.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mv {
+
+constexpr int kTileV = 256;        // vertices per CTA tile == threads per CTA
+constexpr int kECap = 4096;        // edges staged in shared memory per sub-range
+constexpr int kMaxRanks = 16;
+
+struct Edge16 { long long tail; double weight; };          // reference graph.hpp:60-66
+struct CommW { long long size; double degree; };           // reference dspl.hpp:61-66
+
+struct Acc {                       // per-iteration accumulators (one record per iteration, never reset)
+  unsigned long long le_u;         // unit path: sum of counter[0] (dspl.hpp:318, 431)
+  unsigned long long la2_u;        // unit path: sum of degree^2 (dspl.hpp:432)
+  double le_d, la2_d;              // weighted path
+  unsigned long long moved, hash;  // trace (optional)
+};
+
+struct PeerTable {                 // where community y lives: owner rank + that rank's arrays
+  int nranks, rank;
+  long long parts[kMaxRanks + 1];
+  const unsigned long long *cinfo[kMaxRanks];
+  unsigned long long *upd[kMaxRanks];
+  const CommW *cinfo_w[kMaxRanks];
+  long long *usize[kMaxRanks];
+  double *udeg[kMaxRanks];
+};
+
+struct ScanParams {
+  int lnv;
+  int has_self;                    // any self loop in the shard (uniform branch)
+  int heavy_deg;                   // degree > heavy_deg is left to the high-degree kernel (<= kECap)
+  long long base;                  // global id of local vertex 0
+  const uint32_t *rowptr;
+  const int32_t *tails;
+  const double *weights;
+  const int32_t *cur;
+  int32_t *tgt;
+  const int32_t *self_i;           // unit: self-loop count per vertex
+  const double *self_d;            // weighted: truncated self-loop weight (dspl.hpp:285)
+  const double *vdeg;              // weighted: vertex degree (dspl.hpp:82-107)
+  double constant;                 // 1/(2m) (dspl.hpp:129)
+  Acc *acc;
+  // high-degree scratch
+  const int32_t *heavy_list;
+  const unsigned long long *heavy_off;   // table offsets (entries), heavy_count+1
+  int32_t *hkeys;
+  double *hvals_d;
+  int32_t *hvals_i;
+  PeerTable pt;
+};
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long vhash(long long gid, long long val) {
+  return mix64(((unsigned long long)gid) * 0x9E3779B97F4A7C15ULL ^ (unsigned long long)val);
+}
+
+// streaming (read-once) and read-only gathers
+__device__ __forceinline__ int ld_stream(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+template <bool MULTI>
+__device__ __forceinline__ void locate(const PeerTable &pt, long long base, int y, int &owner, long long &idx) {
+  if (!MULTI) { owner = 0; idx = (long long)y - base; return; }
+  int o = 0;
+#pragma unroll 1
+  while (o + 1 < pt.nranks && (long long)y >= pt.parts[o + 1]) o++;
+  owner = o;
+  idx = (long long)y - pt.parts[o];
+}
+
+__device__ __forceinline__ unsigned long long pack_delta(int dsize, long long ddeg) {
+  return (unsigned long long)(((long long)dsize << 32) + ddeg);
+}
+
+// dspl.hpp:212 with the reference's evaluation order and no FMA contraction:
+//   curGain = 2.0*(eiy-eix) - ((2.0*vDegree)*(ay-ax))*constant
+__device__ __forceinline__ double gain_of(double eiy, double eix, double vdeg, double ay, double ax, double c) {
+  const double t1 = __dmul_rn(2.0, __dsub_rn(eiy, eix));
+  const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), __dsub_rn(ay, ax)), c);
+  return __dsub_rn(t1, t2);
+}
+
+// (gain, id) ordering of dspl.hpp:214-215: larger gain wins; equal non-zero gains -> smaller id.
+__device__ __forceinline__ bool better(double g, int y, double bg, int by) {
+  return (g > bg) || ((g == bg) && (g != 0.0) && (y < by));
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// The neighbour-scan kernel: distExecuteLouvainIteration + distBuildLocalMapCounter +
+// distGetMaxIndex (dspl.hpp:276-405, 230-274, 174-228) for every vertex of the shard.
+//
+// One CTA owns a tile of 256 consecutive vertices; their CSR edges are one contiguous range.
+//   phase A (edge-parallel, all 256 lanes busy, coalesced): stream the int32 tails of the tile,
+//           gather cur[tail] (the only random access per edge; 4 B from an L2-resident array) and
+//           stage the neighbour communities (and weights) in shared memory;
+//   phase B (vertex-parallel): each thread reduces its vertex's staged segment to
+//           (community, weight-sum) pairs in place -- sums in edge order, like counter[] in the
+//           reference --, gathers Comm{size,degree} once per distinct community, evaluates dQ with
+//           the reference's exact fp64 rounding sequence, applies the tie-break and the singleton
+//           veto, writes targetComm and pushes the +/- deltas with one (unit) or two (weighted)
+//           atomics per touched community (local HBM or the owner GPU's memory over NVLink).
+// Tiles with more than kECap edges are processed in several sub-ranges; vertices with more than
+// heavy_deg edges are skipped here and handled by k_scan_heavy.
+// ----------------------------------------------------------------------------------------------
+template <bool UNIT, bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);                       // kECap
+  int32_t *s_cnt = s_comm + kECap;                                               // unit: kECap counts
+  double *s_w = reinterpret_cast<double *>(smem_raw + sizeof(int32_t) * kECap);  // weighted: kECap sums
+  __shared__ int s_next;
+  __shared__ unsigned long long s_red[3][kTileV / 32];
+  __shared__ double s_redd[kTileV / 32];
+
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileV;
+  const int v1 = min(p.lnv, v0 + kTileV);
+  const int v = v0 + tid;
+  uint32_t r0 = 0, r1 = 0;
+  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
+  const uint32_t deg = r1 - r0;
+  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
+
+  unsigned long long acc_le_u = 0, acc_moved = 0, acc_hash = 0;
+  double acc_le_d = 0.0;
+
+  int start = v0;
+  while (start < v1) {
+    // ---- choose the sub-range [start, end): longest run of non-heavy vertices whose edges fit the buffer
+    __shared__ uint32_t s_e0;
+    __shared__ int s_skip, s_end;
+    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; }
+    __syncthreads();
+    if (s_skip) { start++; __syncthreads(); continue; }
+    const uint32_t E0 = s_e0;
+    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
+    __syncthreads();
+    const int end = s_end;                         // > start: the start vertex itself always fits
+    if (tid == end - 1 - v0) s_next = (int)r1;     // last vertex of the sub-range publishes E1
+    __syncthreads();
+    const uint32_t E1 = (uint32_t)s_next;
+    const int ne = (int)(E1 - E0);
+
+    // ---- phase A: stage neighbour communities (and weights)
+    {
+      const int32_t *tl = p.tails + E0;
+      int i = tid;
+      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
+        const int t0 = ld_stream(tl + i), t1 = ld_stream(tl + i + kTileV), t2 = ld_stream(tl + i + 2 * kTileV),
+                  t3 = ld_stream(tl + i + 3 * kTileV);
+        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
+        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      }
+      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_stream(tl + i));
+      if (!UNIT) {
+        const double *wl = p.weights + E0;
+        for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B: one thread per vertex of the sub-range
+    if (v >= start && v < end) {
+      const int cc = __ldg(p.cur + v);
+      int best = cc;
+      if (deg != 0) {
+        const int o0 = (int)(r0 - E0);
+        const int d = (int)deg;
+        int nd = 0;
+        // own-community Comm{size,degree}
+        int owner; long long idx;
+        locate<MULTI>(p.pt, p.base, cc, owner, idx);
+        double vdeg, eix, ax, cc_deg; long long cc_size;
+        if (UNIT) {
+          int cnt0 = 0;
+          for (int k = 0; k < d; k++) {
+            const int ck = s_comm[o0 + k];
+            if (ck == cc) { cnt0++; continue; }
+            if (ck < 0) continue;
+            int c = 1;
+            for (int j = k + 1; j < d; j++)
+              if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
+            s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
+          }
+          const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[owner] : p.pt.cinfo[0]) + idx);
+          cc_size = (long long)(ci >> 32);
+          cc_deg = (double)(uint32_t)ci;
+          vdeg = (double)d;
+          const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
+          eix = (double)(cnt0 - sl);
+          acc_le_u += (unsigned long long)cnt0;
+        } else {
+          double w0 = 0.0;                                   // counter[0] starts at 0.0 (dspl.hpp:313)
+          for (int k = 0; k < d; k++) {
+            const int ck = s_comm[o0 + k];
+            if (ck == cc) { w0 += s_w[o0 + k]; continue; }
+            if (ck < 0) continue;
+            double sum = s_w[o0 + k];
+            for (int j = k + 1; j < d; j++)
+              if (s_comm[o0 + j] == ck) { sum += s_w[o0 + j]; s_comm[o0 + j] = -1; }
+            s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
+          }
+          const CommW *cw = (MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx;
+          const double2 raw = __ldg(reinterpret_cast<const double2 *>(cw));
+          cc_size = __double_as_longlong(raw.x);
+          cc_deg = raw.y;
+          vdeg = __ldg(p.vdeg + v);
+          const double sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
+          eix = __dsub_rn(w0, sl);
+          acc_le_d += w0;
+        }
+        ax = __dsub_rn(cc_deg, vdeg);
+        double best_gain = 0.0;
+        long long best_size = cc_size;
+        for (int m = 0; m < nd; m++) {
+          const int y = s_comm[o0 + m];
+          int yo; long long yi;
+          locate<MULTI>(p.pt, p.base, y, yo, yi);
+          double ay, eiy; long long ysize;
+          if (UNIT) {
+            const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[yo] : p.pt.cinfo[0]) + yi);
+            ysize = (long long)(ci >> 32);
+            ay = (double)(uint32_t)ci;
+            eiy = (double)s_cnt[o0 + m];
+          } else {
+            const double2 raw = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi));
+            ysize = __double_as_longlong(raw.x);
+            ay = raw.y;
+            eiy = s_w[o0 + m];
+          }
+          const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
+          if (better(g, y, best_gain, best)) { best_gain = g; best = y; best_size = ysize; }
+        }
+        if (best_size == 1 && cc_size == 1 && best > cc) best = cc;          // dspl.hpp:224-225
+        if (best != cc) {                                                    // dspl.hpp:331-399
+          int bo; long long bi;
+          locate<MULTI>(p.pt, p.base, best, bo, bi);
+          if (UNIT) {
+            atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)d));
+            atomicAdd((MULTI ? p.pt.upd[owner] : p.pt.upd[0]) + idx, pack_delta(-1, -(long long)d));
+          } else {
+            atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
+            atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
+            atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[owner] : p.pt.usize[0]) + idx), ~0ULL);
+            atomicAdd((MULTI ? p.pt.udeg[owner] : p.pt.udeg[0]) + idx, -vdeg);
+          }
+        }
+      }
+      p.tgt[v] = best;                                                       // dspl.hpp:404
+      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(p.base + v, best); }
+    }
+    start = end;
+    __syncthreads();
+  }
+
+  // ---- CTA reduction of the modularity / trace partial sums, one atomic each per CTA
+  const int lane = tid & 31, wid = tid >> 5;
+  if (UNIT) { const unsigned long long s = warp_sum(acc_le_u); if (lane == 0) s_red[0][wid] = s; }
+  else { const double s = warp_sum(acc_le_d); if (lane == 0) s_redd[wid] = s; }
+  if (TRACE) {
+    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
+    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (UNIT) {
+      unsigned long long s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
+      if (s) atomicAdd(&p.acc->le_u, s);
+    } else {
+      double s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
+      if (s != 0.0) atomicAdd(&p.acc->le_d, s);
+    }
+    if (TRACE) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
+      atomicAdd(&p.acc->moved, a);
+      atomicAdd(&p.acc->hash, b);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// High-degree vertices (degree > heavy_deg): one CTA per vertex, open-addressing table in HBM
+// scratch (2x degree entries) keyed by neighbour community; same decision rule.  Weighted sums are
+// accumulated with fp64 atomics here (order not fixed: weighted parity is tolerance-based anyway).
+// ----------------------------------------------------------------------------------------------
+template <bool UNIT, bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
+  const int v = p.heavy_list[blockIdx.x];
+  const unsigned long long off = p.heavy_off[blockIdx.x];
+  const unsigned int T = (unsigned int)(p.heavy_off[blockIdx.x + 1] - off);   // power of two
+  int32_t *keys = p.hkeys + off;
+  int32_t *vi = UNIT ? p.hvals_i + off : nullptr;
+  double *vd = UNIT ? nullptr : p.hvals_d + off;
+  const int tid = threadIdx.x;
+  const uint32_t e0 = p.rowptr[v], e1 = p.rowptr[v + 1];
+  const int cc = p.cur[v];
+  for (unsigned int i = tid; i < T; i += blockDim.x) { keys[i] = -1; if (UNIT) vi[i] = 0; else vd[i] = 0.0; }
+  __syncthreads();
+  for (uint32_t e = e0 + tid; e < e1; e += blockDim.x) {
+    const int c = __ldg(p.cur + p.tails[e]);
+    unsigned int h = (unsigned int)mix64((unsigned long long)c) & (T - 1);
+    for (;;) {
+      const int old = atomicCAS(&keys[h], -1, c);
+      if (old == -1 || old == c) {
+        if (UNIT) atomicAdd(&vi[h], 1); else atomicAdd(&vd[h], p.weights[e]);
+        break;
+      }
+      h = (h + 1) & (T - 1);
+    }
+  }
+  __syncthreads();
+  __shared__ double s_w0;
+  __shared__ double s_g[8];
+  __shared__ int s_y[8];
+  __shared__ long long s_sz[8];
+  if (tid == 0) s_w0 = 0.0;
+  __syncthreads();
+  for (unsigned int i = tid; i < T; i += blockDim.x)
+    if (keys[i] == cc) s_w0 = UNIT ? (double)vi[i] : vd[i];
+  __syncthreads();
+  int owner; long long idx;
+  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  double cc_deg, vdeg, sl; long long cc_size;
+  if (UNIT) {
+    const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[owner] : p.pt.cinfo[0]) + idx);
+    cc_size = (long long)(ci >> 32); cc_deg = (double)(uint32_t)ci;
+    vdeg = (double)(e1 - e0);
+    sl = p.has_self ? (double)p.self_i[v] : 0.0;
+  } else {
+    const CommW cw = (MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0])[idx];
+    cc_size = cw.size; cc_deg = cw.degree;
+    vdeg = p.vdeg[v];
+    sl = p.has_self ? p.self_d[v] : 0.0;
+  }
+  const double w0 = s_w0;
+  const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
+  double bg = 0.0; int by = cc; long long bsz = cc_size;
+  for (unsigned int i = tid; i < T; i += blockDim.x) {
+    const int y = keys[i];
+    if (y < 0 || y == cc) continue;
+    int yo; long long yi;
+    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    double ay, eiy; long long ysz;
+    if (UNIT) {
+      const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[yo] : p.pt.cinfo[0]) + yi);
+      ysz = (long long)(ci >> 32); ay = (double)(uint32_t)ci; eiy = (double)vi[i];
+    } else {
+      const CommW cw = (MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0])[yi];
+      ysz = cw.size; ay = cw.degree; eiy = vd[i];
+    }
+    const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
+    if (better(g, y, bg, by)) { bg = g; by = y; bsz = ysz; }
+  }
+  // CTA argmax under the same ordering.  `better` needs care when combining partial winners that
+  // still sit at the initial state (gain 0, id cc): an initial state never beats a real candidate.
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, bg, o);
+    const int oy = __shfl_xor_sync(0xffffffffu, by, o);
+    const long long os = __shfl_xor_sync(0xffffffffu, bsz, o);
+    if (oy != cc && (by == cc || better(og, oy, bg, by))) { bg = og; by = oy; bsz = os; }
+  }
+  if ((tid & 31) == 0) { s_g[tid >> 5] = bg; s_y[tid >> 5] = by; s_sz[tid >> 5] = bsz; }
+  __syncthreads();
+  if (tid == 0) {
+    bg = 0.0; by = cc; bsz = cc_size;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++)
+      if (s_y[w] != cc && (by == cc || better(s_g[w], s_y[w], bg, by))) { bg = s_g[w]; by = s_y[w]; bsz = s_sz[w]; }
+    int best = by;
+    if (bsz == 1 && cc_size == 1 && best > cc) best = cc;
+    if (best != cc) {
+      int bo; long long bi;
+      locate<MULTI>(p.pt, p.base, best, bo, bi);
+      if (UNIT) {
+        atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)(e1 - e0)));
+        atomicAdd((MULTI ? p.pt.upd[owner] : p.pt.upd[0]) + idx, pack_delta(-1, -(long long)(e1 - e0)));
+      } else {
+        atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
+        atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
+        atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[owner] : p.pt.usize[0]) + idx), ~0ULL);
+        atomicAdd((MULTI ? p.pt.udeg[owner] : p.pt.udeg[0]) + idx, -vdeg);
+      }
+    }
+    p.tgt[v] = best;
+    if (UNIT) atomicAdd(&p.acc->le_u, (unsigned long long)w0); else atomicAdd(&p.acc->le_d, w0);
+    if (TRACE) { atomicAdd(&p.acc->moved, (unsigned long long)(best != cc)); atomicAdd(&p.acc->hash, vhash(p.base + v, best)); }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fold kernel: localCinfo += localCupdate (+ the deltas remote ranks pushed with NVLink atomics,
+// i.e. updateRemoteCommunities), zero the update array for the next iteration (distCleanCWandCU)
+// and accumulate sum(degree^2) for the modularity (dspl.hpp:458-471, 978-1103, 473-486, 432).
+// ----------------------------------------------------------------------------------------------
+template <bool UNIT>
+__global__ void __launch_bounds__(256) k_fold(int lnv, unsigned long long *cinfo, unsigned long long *upd, CommW *cinfo_w,
+                                              long long *usize, double *udeg, Acc *acc) {
+  unsigned long long a2u = 0;
+  double a2d = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lnv; i += gridDim.x * blockDim.x) {
+    if (UNIT) {
+      unsigned long long c = cinfo[i];
+      const unsigned long long u = upd[i];
+      if (u) { c += u; cinfo[i] = c; upd[i] = 0; }
+      const unsigned long long d = (uint32_t)c;
+      a2u += d * d;
+    } else {
+      CommW c = cinfo_w[i];
+      const long long us = usize[i];
+      const double ud = udeg[i];
+      if (us != 0 || ud != 0.0) {
+        c.size += us; c.degree += ud;
+        cinfo_w[i] = c; usize[i] = 0; udeg[i] = 0.0;
+      }
+      a2d += c.degree * c.degree;
+    }
+  }
+  __shared__ unsigned long long su[8];
+  __shared__ double sd[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (UNIT) { const unsigned long long s = warp_sum(a2u); if (lane == 0) su[wid] = s; }
+  else { const double s = warp_sum(a2d); if (lane == 0) sd[wid] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (UNIT) { unsigned long long s = 0; for (int w = 0; w < 8; w++) s += su[w]; atomicAdd(&acc->la2_u, s); }
+    else { double s = 0; for (int w = 0; w < 8; w++) s += sd[w]; atomicAdd(&acc->la2_d, s); }
+  }
+}
+
+// Modularity partials as doubles for the cross-rank all-reduce (MPI_Allreduce of 2 doubles, dspl.hpp:441).
+__global__ void k_acc_to_double(const Acc *acc, int unit, double *out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    out2[0] = unit ? (double)acc->le_u : acc->le_d;
+    out2[1] = unit ? (double)acc->la2_u : acc->la2_d;
+  }
+}
+__global__ void k_trace_to_u64(const Acc *acc, unsigned long long *out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out2[0] = acc->moved; out2[1] = acc->hash; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Setup kernels (once per run): format conversion, ghost discovery, init (dspl.hpp:1106-1272, 151-172)
+// ----------------------------------------------------------------------------------------------
+struct EdgeStats { unsigned long long nremote; unsigned int nonunit; unsigned int bad_tail; };
+
+__global__ void __launch_bounds__(256) k_edge_stats(const Edge16 *edges, long long lne, long long base, long long bound,
+                                                    long long nv_global, EdgeStats *st) {
+  unsigned long long nrem = 0;
+  unsigned int nonunit = 0, bad = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
+    const double2 raw = __ldcs(reinterpret_cast<const double2 *>(edges + e));
+    const long long t = __double_as_longlong(raw.x);
+    if (raw.y != 1.0) nonunit = 1;
+    if (t < 0 || t >= nv_global) bad = 1;
+    else if (t < base || t >= bound) nrem++;
+  }
+  nrem = warp_sum(nrem);
+  nonunit = __any_sync(0xffffffffu, nonunit);
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (nrem) atomicAdd(&st->nremote, nrem);
+    if (nonunit) atomicOr(&st->nonunit, 1u);
+    if (bad) atomicOr(&st->bad_tail, 1u);
+  }
+}
+
+// tails -> local slot (ghosts provisionally -1), weights split off, remote tails appended to a list
+__global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long long lne, long long base, long long bound,
+                                                       int32_t *tails, double *weights, long long *remote_list,
+                                                       unsigned long long *remote_cursor) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
+    const double2 raw = __ldcs(reinterpret_cast<const double2 *>(edges + e));
+    const long long t = __double_as_longlong(raw.x);
+    const bool local = (t >= base && t < bound);
+    tails[e] = local ? (int32_t)(t - base) : -1;
+    if (weights) weights[e] = raw.y;
+    if (!local && remote_list) {
+      const unsigned long long pos = atomicAdd(remote_cursor, 1ULL);
+      remote_list[pos] = t;
+    }
+  }
+}
+
+// ghosts: slot = lnv + rank of the tail in the sorted unique ghost list
+__global__ void __launch_bounds__(256) k_remap_ghost_tails(const Edge16 *edges, long long lne, int32_t *tails,
+                                                           const long long *ghost_gid, int nghost, int lnv) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
+    if (tails[e] >= 0) continue;
+    const long long t = edges[e].tail;
+    int lo = 0, hi = nghost;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ghost_gid[mid] < t) lo = mid + 1; else hi = mid; }
+    tails[e] = lnv + lo;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int lnv, uint32_t *rowptr, unsigned int *maxdeg,
+                                                  unsigned int *bad) {
+  unsigned int md = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= lnv; i += gridDim.x * blockDim.x) {
+    const long long r = rowptr64[i];
+    rowptr[i] = (uint32_t)r;
+    if (i < lnv) {
+      const long long d = rowptr64[i + 1] - r;
+      if (d < 0) *bad = 1;
+      else md = max(md, (unsigned int)min(d, (long long)0xffffffffu));
+    }
+  }
+  for (int o = 16; o; o >>= 1) md = max(md, __shfl_xor_sync(0xffffffffu, md, o));
+  if ((threadIdx.x & 31) == 0 && md) atomicMax(maxdeg, md);
+}
+
+// distSumVertexDegree + distInitComm + self-loop weights (dspl.hpp:82-107, 132-149, 247-248/285)
+template <bool UNIT>
+__global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, const uint32_t *rowptr, const int32_t *tails,
+                                                     const double *weights, int32_t *cur, unsigned long long *cinfo,
+                                                     unsigned long long *upd, CommW *cinfo_w, long long *usize, double *udeg,
+                                                     double *vdeg, int32_t *self_i, double *self_d, double *total_weight,
+                                                     unsigned int *has_self) {
+  double tw_sum = 0.0;
+  unsigned int any_self = 0;
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
+    const uint32_t e0 = rowptr[v], e1 = rowptr[v + 1];
+    cur[v] = (int32_t)(base + v);
+    if (UNIT) {
+      int sl = 0;
+      for (uint32_t e = e0; e < e1; e++) sl += (tails[e] == v);
+      self_i[v] = sl;
+      any_self |= (sl != 0);
+      cinfo[v] = (1ULL << 32) | (unsigned long long)(e1 - e0);
+      upd[v] = 0;
+      tw_sum += (double)(e1 - e0);
+    } else {
+      double tw = 0.0, sl = 0.0;
+      for (uint32_t e = e0; e < e1; e++) {           // edge order, like dspl.hpp:97-100
+        const double w = weights[e];
+        tw += w;
+        if (tails[e] == v) sl += w;
+      }
+      vdeg[v] = tw;
+      self_d[v] = (double)(long long)sl;             // GraphWeight -> GraphElem truncation (dspl.hpp:285,315)
+      any_self |= (sl != 0.0);
+      CommW c; c.size = 1; c.degree = tw;
+      cinfo_w[v] = c;
+      usize[v] = 0; udeg[v] = 0.0;
+      tw_sum += tw;
+    }
+  }
+  tw_sum = warp_sum(tw_sum);
+  any_self = __any_sync(0xffffffffu, any_self);
+  if ((threadIdx.x & 31) == 0) {
+    if (tw_sum != 0.0) atomicAdd(total_weight, tw_sum);
+    if (any_self) atomicOr(has_self, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *rowptr, unsigned int heavy_deg, int32_t *list,
+                                                       unsigned int *count) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x)
+    if (rowptr[v + 1] - rowptr[v] > heavy_deg) list[atomicAdd(count, 1u)] = v;
+}
+
+// ghost exchange helpers (dspl.hpp:559-571): pack the communities peers asked for; global -> local ids
+__global__ void __launch_bounds__(256) k_pack_send(const int32_t *comm, const int32_t *send_lid, int n, int32_t *out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = comm[send_lid[i]];
+}
+__global__ void __launch_bounds__(256) k_gid_to_lid(const long long *gid, int n, long long base, int32_t *lid) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) lid[i] = (int32_t)(gid[i] - base);
+}
+__global__ void __launch_bounds__(256) k_init_ghost_comm(const long long *ghost_gid, int n, int32_t *comm_ghost) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) comm_ghost[i] = (int32_t)ghost_gid[i];
+}
+
+}  // namespace mv

@@ -1,0 +1,776 @@
+// libmvgpu.so: the B200 implementation behind include/mvgpu.h.
+//
+// Replaces miniVite's distLouvainMethod (reference dspl.hpp:1280-1441) for one rank == one GPU:
+//   setup      format conversion + ghost discovery + init   (dspl.hpp:1106-1272, 151-172)
+//   iteration  scan kernel -> [ghost exchange, barrier] -> fold kernel -> [all-reduce] -> host test
+// Multi-GPU: vertex-range shards; the per-iteration ghost vertex->community map moves as a grouped
+// ncclSend/ncclRecv all-to-all-v with run-constant counts straight into the ghost tail of the
+// community array; Comm{size,degree} of remotely owned communities is read, and their deltas are
+// pushed, directly in the owner's HBM over NVLink (peer pointers obtained through CUDA IPC), which
+// removes the reference's request/reply and delta-push message rounds (dspl.hpp:719-929, 1022-1102);
+// modularity is one ncclAllReduce of two doubles (dspl.hpp:441).
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/mvgpu.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace {
+
+thread_local std::string g_err;
+mvnccl::Api g_nccl;
+
+int fail(const std::string &msg) { g_err = msg; return 1; }
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess)                                                                         \
+      return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_) return rc_;     \
+  } while (0)
+
+template <typename T>
+struct DevBuf {              // grow-only device buffer (allocations are cached across runs)
+  T *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (n == 0) n = 1;
+    CK(cudaMalloc(&p, n * sizeof(T)));
+    cap = n;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PeerBlob {            // what every rank publishes about its community arrays
+  cudaIpcMemHandle_t h[5];
+  unsigned long long raw[5];
+  int pid, device, unit, pad;
+};
+
+}  // namespace
+
+using namespace mv;
+
+struct mvgpu_ctx {
+  int device = 0, rank = 0, nranks = 1;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  // communicator
+  ncclComm_t comm = nullptr;
+  // input (reference format, device)
+  long long nv_global = 0, lnv = 0, lne = 0, base = 0, bound = 0;
+  std::vector<long long> parts;
+  const long long *d_rowptr64 = nullptr;
+  const Edge16 *d_edges = nullptr;
+  DevBuf<long long> in_rowptr;
+  DevBuf<Edge16> in_edges;
+  bool have_graph = false;
+  // compact graph
+  DevBuf<uint32_t> rowptr;
+  DevBuf<int32_t> tails;
+  DevBuf<double> weights;
+  DevBuf<int32_t> self_i;
+  DevBuf<double> self_d, vdeg;
+  // state
+  DevBuf<int32_t> comm_a, comm_b;
+  DevBuf<unsigned long long> cinfo, upd;
+  DevBuf<CommW> cinfo_w;
+  DevBuf<long long> usize;
+  DevBuf<double> udeg;
+  DevBuf<Acc> acc;
+  DevBuf<unsigned char> scratch;       // small device scalars
+  DevBuf<unsigned char> cub_tmp;
+  // ghosts
+  DevBuf<long long> remote_list, ghost_gid, send_gid;
+  DevBuf<int32_t> send_lid, send_buf;
+  long long nghost = 0, nsend = 0;
+  std::vector<long long> rcount, scount, roff, soff;   // per peer
+  // heavy vertices
+  DevBuf<int32_t> heavy_list, hkeys, hvals_i;
+  DevBuf<double> hvals_d;
+  DevBuf<unsigned long long> heavy_off;
+  long long nheavy = 0, maxdeg = 0;
+  int scan_has_self = 0, scan_heavy_deg = kECap;
+  // peers
+  PeerTable pt;
+  std::vector<void *> ipc_opened;
+  bool peers_ready = false;
+  int peers_unit = -1;
+  // options
+  int opt_trace = 0, opt_force_weighted = 0;
+  long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
+  // results
+  bool unit = true;
+  double constant = 0.0;
+  int32_t *d_final = nullptr;          // currComm at exit (points into comm_a/comm_b)
+  std::vector<mvgpu_iter_trace> trace;
+  mvgpu_timings tm;
+  double h2d_s = 0.0;
+  // pinned host mailbox
+  void *h_pin = nullptr;
+  // events
+  std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+int grid_for(long long n, int threads, int num_sms, int per_sm = 8) {
+  long long b = (n + threads - 1) / threads;
+  long long cap = (long long)num_sms * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+cudaEvent_t get_event(mvgpu_ctx *c, size_t i) {
+  while (c->events.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->events.push_back(e);
+  }
+  return c->events[i];
+}
+
+// device scalar slots inside c->scratch
+struct Scalars {
+  EdgeStats st;
+  unsigned long long remote_cursor;
+  unsigned int maxdeg, bad_rowptr, has_self, heavy_count;
+  int nunique;
+  int pad;
+  double total_weight;
+  double red2[2];
+  unsigned long long tr2[2];
+  long long counts[2 * kMaxRanks];
+};
+
+int set_graph(mvgpu_ctx *c, long long nv_global, const int64_t *parts, long long lnv, long long lne) {
+  if (c->nranks > kMaxRanks) return fail("too many ranks");
+  if (nv_global < 0 || lnv < 0 || lne < 0) return fail("negative graph size");
+  if (nv_global >= (1LL << 31)) return fail("nv_global >= 2^31: 32-bit community ids would overflow (not supported)");
+  if (lne >= (1LL << 32)) return fail("lne >= 2^32 per shard: 32-bit edge offsets would overflow (not supported)");
+  c->parts.assign(parts, parts + c->nranks + 1);
+  if (c->parts[0] != 0 || c->parts[c->nranks] != nv_global) return fail("parts[] must run from 0 to nv_global");
+  for (int r = 0; r < c->nranks; r++) if (c->parts[r + 1] < c->parts[r]) return fail("parts[] not monotone");
+  c->base = c->parts[c->rank];
+  c->bound = c->parts[c->rank + 1];
+  if (c->bound - c->base != lnv) return fail("lnv does not match parts[rank+1]-parts[rank]");
+  c->nv_global = nv_global; c->lnv = lnv; c->lne = lne;
+  c->have_graph = true;
+  c->peers_ready = false;
+  return 0;
+}
+
+// ---- multi-GPU: publish/obtain peer pointers for the community arrays -------------------------
+int setup_peers(mvgpu_ctx *c, int unit) {
+  PeerTable &pt = c->pt;
+  pt.nranks = c->nranks; pt.rank = c->rank;
+  for (int r = 0; r <= c->nranks; r++) pt.parts[r] = c->parts[r];
+  if (c->nranks == 1) {
+    pt.cinfo[0] = c->cinfo.p; pt.upd[0] = c->upd.p; pt.cinfo_w[0] = c->cinfo_w.p; pt.usize[0] = c->usize.p; pt.udeg[0] = c->udeg.p;
+    return 0;
+  }
+  if (c->peers_ready && c->peers_unit == unit) return 0;
+  for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  c->ipc_opened.clear();
+  PeerBlob mine;
+  memset(&mine, 0, sizeof mine);
+  void *ptrs[5] = {unit ? (void *)c->cinfo.p : nullptr, unit ? (void *)c->upd.p : nullptr,
+                   unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
+                   unit ? nullptr : (void *)c->udeg.p};
+  for (int k = 0; k < 5; k++) {
+    mine.raw[k] = (unsigned long long)ptrs[k];
+    if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
+  }
+  mine.pid = (int)getpid(); mine.device = c->device; mine.unit = unit;
+  DevBuf<PeerBlob> d_all;
+  TRY(d_all.ensure(c->nranks + 1));
+  CK(cudaMemcpyAsync(d_all.p + c->nranks, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(d_all.p + c->nranks, d_all.p, sizeof(PeerBlob), ncclChar, c->comm, c->stream));
+  std::vector<PeerBlob> all(c->nranks);
+  CK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(PeerBlob) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  d_all.release();
+  for (int r = 0; r < c->nranks; r++) {
+    void *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (all[r].unit != unit) return fail("ranks disagree on the unit-weight path");
+    if (r == c->rank) { for (int k = 0; k < 5; k++) q[k] = ptrs[k]; }
+    else if (all[r].pid == mine.pid) {           // same process (threads): plain UVA pointers + peer access
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
+      if (!can) return fail("GPU " + std::to_string(c->device) + " cannot access peer GPU " + std::to_string(all[r].device));
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+      cudaGetLastError();
+      for (int k = 0; k < 5; k++) q[k] = (void *)all[r].raw[k];
+    } else {
+      for (int k = 0; k < 5; k++)
+        if (all[r].raw[k]) {
+          CK(cudaIpcOpenMemHandle(&q[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess));
+          c->ipc_opened.push_back(q[k]);
+        }
+    }
+    pt.cinfo[r] = (const unsigned long long *)q[0]; pt.upd[r] = (unsigned long long *)q[1];
+    pt.cinfo_w[r] = (const CommW *)q[2]; pt.usize[r] = (long long *)q[3]; pt.udeg[r] = (double *)q[4];
+  }
+  c->peers_ready = true;
+  c->peers_unit = unit;
+  return 0;
+}
+
+template <bool UNIT, bool MULTI, bool TRACE>
+int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
+  const size_t smem = UNIT ? sizeof(int32_t) * 2 * kECap : sizeof(int32_t) * kECap + sizeof(double) * kECap;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CK(cudaFuncSetAttribute(k_scan<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
+  if (tiles > 0) {
+    k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    c->tm.kernel_launches++; c->tm.scan_launches++;
+  }
+  if (c->nheavy > 0) {
+    k_scan_heavy<UNIT, MULTI, TRACE><<<(int)c->nheavy, 256, 0, c->stream>>>(sp);
+    c->tm.kernel_launches++; c->tm.scan_launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int launch_scan(mvgpu_ctx *c, const ScanParams &sp) {
+  const bool multi = c->nranks > 1, tr = c->opt_trace != 0;
+#define MV_CASE(U, M, T) if (c->unit == U && multi == M && tr == T) return launch_scan_t<U, M, T>(c, sp);
+  MV_CASE(true, false, false) MV_CASE(true, false, true) MV_CASE(true, true, false) MV_CASE(true, true, true)
+  MV_CASE(false, false, false) MV_CASE(false, false, true) MV_CASE(false, true, false) MV_CASE(false, true, true)
+#undef MV_CASE
+  return fail("unreachable");
+}
+
+// ---- setup: reference-format arrays -> compact graph, ghosts, init ------------------------------
+int setup_run(mvgpu_ctx *c) {
+  cudaStream_t s = c->stream;
+  const int nsm = c->num_sms;
+  TRY(c->scratch.ensure(sizeof(Scalars)));
+  Scalars *d_sc = reinterpret_cast<Scalars *>(c->scratch.p);
+  Scalars h;
+  CK(cudaMemsetAsync(d_sc, 0, sizeof(Scalars), s));
+  const long long lnv = c->lnv, lne = c->lne;
+
+  // pass 1 over the edges: unit weights? how many non-owned tails? (+ input validation)
+  k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
+  c->tm.kernel_launches++;
+  TRY(c->rowptr.ensure(lnv + 1));
+  k_rowptr32<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>(c->d_rowptr64, (int)lnv, c->rowptr.p, &d_sc->maxdeg, &d_sc->bad_rowptr);
+  c->tm.kernel_launches++;
+  CK(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h.st.bad_tail) return fail("edge tail outside [0, nv)");
+  if (h.bad_rowptr) return fail("edge_indices not monotone");
+  if (c->nranks == 1 && h.st.nremote) return fail("non-local tail in a single-rank graph");
+  c->maxdeg = h.maxdeg;
+  int unit = (!h.st.nonunit && !c->opt_force_weighted) ? 1 : 0;
+
+  // global agreement on the path + on 2m < 2^31 needs the total weight; the weight total itself comes
+  // from the vertex-init kernel below, so first settle `unit` from the flags (ne bound checked after).
+  long long ne_global = lne;
+  if (c->nranks > 1) {
+    long long hv[2] = {unit ? 0 : 1, lne};
+    CK(cudaMemcpyAsync(d_sc->counts, hv, sizeof hv, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 2, ncclInt64, ncclSum, c->comm, s));
+    CK(cudaMemcpyAsync(hv, d_sc->counts, sizeof hv, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    unit = hv[0] == 0;
+    ne_global = hv[1];
+  }
+  if (unit && ne_global >= (1LL << 31)) unit = 0;   // packed 32-bit degree deltas need 2m < 2^31
+  c->unit = unit != 0;
+
+  // pass 2: tails -> slots, weights split off, remote tails listed
+  TRY(c->tails.ensure(lne));
+  if (!c->unit) TRY(c->weights.ensure(lne));
+  const long long nremote = (long long)h.st.nremote;
+  if (nremote) TRY(c->remote_list.ensure(nremote));
+  k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->tails.p,
+                                                            c->unit ? nullptr : c->weights.p,
+                                                            nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
+  c->tm.kernel_launches++;
+
+  // ghost discovery (exchangeVertexReqs, dspl.hpp:1106-1272): sorted unique non-owned tails
+  c->nghost = 0; c->nsend = 0;
+  c->rcount.assign(c->nranks, 0); c->scount.assign(c->nranks, 0);
+  c->roff.assign(c->nranks + 1, 0); c->soff.assign(c->nranks + 1, 0);
+  if (c->nranks > 1) {
+    if (nremote) {
+      DevBuf<long long> sorted;
+      TRY(sorted.ensure(nremote));
+      TRY(c->ghost_gid.ensure(nremote));
+      size_t tb1 = 0, tb2 = 0;
+      int bits = 1;
+      while ((1LL << bits) < c->nv_global && bits < 63) bits++;
+      cub::DeviceRadixSort::SortKeys(nullptr, tb1, c->remote_list.p, sorted.p, nremote, 0, bits, s);
+      cub::DeviceSelect::Unique(nullptr, tb2, sorted.p, c->ghost_gid.p, &d_sc->nunique, nremote, s);
+      TRY(c->cub_tmp.ensure(std::max(tb1, tb2)));
+      size_t tb = c->cub_tmp.cap;
+      CK(cub::DeviceRadixSort::SortKeys(c->cub_tmp.p, tb, c->remote_list.p, sorted.p, nremote, 0, bits, s));
+      tb = c->cub_tmp.cap;
+      CK(cub::DeviceSelect::Unique(c->cub_tmp.p, tb, sorted.p, c->ghost_gid.p, &d_sc->nunique, nremote, s));
+      c->tm.kernel_launches += 2;
+      int nu = 0;
+      CK(cudaMemcpyAsync(&nu, &d_sc->nunique, sizeof nu, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      sorted.release();
+      c->nghost = nu;
+      if (lnv + c->nghost >= (1LL << 31)) return fail("lnv + nghost >= 2^31");
+      k_remap_ghost_tails<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
+      c->tm.kernel_launches++;
+      // per-owner counts of my ghosts (the list is sorted, owners are contiguous ranges)
+      std::vector<long long> hg(c->nghost);
+      CK(cudaMemcpyAsync(hg.data(), c->ghost_gid.p, sizeof(long long) * c->nghost, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      for (int r = 0; r < c->nranks; r++) {
+        const long long lo = std::lower_bound(hg.begin(), hg.end(), c->parts[r]) - hg.begin();
+        const long long hi = std::lower_bound(hg.begin(), hg.end(), c->parts[r + 1]) - hg.begin();
+        c->rcount[r] = hi - lo;
+      }
+    }
+    for (int r = 0; r < c->nranks; r++) c->roff[r + 1] = c->roff[r] + c->rcount[r];
+    // tell every owner how many of its vertices I ghost (MPI_Alltoall of sizes, dspl.hpp:1184)
+    long long *d_cnt = d_sc->counts;
+    CK(cudaMemcpyAsync(d_cnt, c->rcount.data(), sizeof(long long) * c->nranks, cudaMemcpyHostToDevice, s));
+    NK(g_nccl.GroupStart());
+    for (int r = 0; r < c->nranks; r++) {
+      NK(g_nccl.Send(d_cnt + r, 1, ncclInt64, r, c->comm, s));
+      NK(g_nccl.Recv(d_cnt + kMaxRanks + r, 1, ncclInt64, r, c->comm, s));
+    }
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(c->scount.data(), d_cnt + kMaxRanks, sizeof(long long) * c->nranks, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int r = 0; r < c->nranks; r++) c->soff[r + 1] = c->soff[r] + c->scount[r];
+    c->nsend = c->soff[c->nranks];
+    // ship the ghost id lists to their owners (dspl.hpp:1228-1252); they become the owners' send lists
+    TRY(c->send_gid.ensure(c->nsend));
+    TRY(c->send_lid.ensure(c->nsend));
+    TRY(c->send_buf.ensure(c->nsend));
+    NK(g_nccl.GroupStart());
+    for (int r = 0; r < c->nranks; r++) {
+      if (r == c->rank) continue;
+      if (c->rcount[r]) NK(g_nccl.Send(c->ghost_gid.p + c->roff[r], c->rcount[r], ncclInt64, r, c->comm, s));
+      if (c->scount[r]) NK(g_nccl.Recv(c->send_gid.p + c->soff[r], c->scount[r], ncclInt64, r, c->comm, s));
+    }
+    NK(g_nccl.GroupEnd());
+    if (c->nsend) {
+      k_gid_to_lid<<<grid_for(c->nsend, 256, nsm), 256, 0, s>>>(c->send_gid.p, (int)c->nsend, c->base, c->send_lid.p);
+      c->tm.kernel_launches++;
+    }
+  }
+
+  // state arrays
+  const long long nslots = lnv + c->nghost;
+  TRY(c->comm_a.ensure(nslots));
+  TRY(c->comm_b.ensure(nslots));
+  if (c->unit) { TRY(c->cinfo.ensure(lnv)); TRY(c->upd.ensure(lnv)); TRY(c->self_i.ensure(lnv)); }
+  else { TRY(c->cinfo_w.ensure(lnv)); TRY(c->usize.ensure(lnv)); TRY(c->udeg.ensure(lnv)); TRY(c->vdeg.ensure(lnv)); TRY(c->self_d.ensure(lnv)); }
+  TRY(c->acc.ensure((size_t)c->opt_max_iters + 2));
+  CK(cudaMemsetAsync(c->acc.p, 0, sizeof(Acc) * ((size_t)c->opt_max_iters + 2), s));
+
+  if (c->unit)
+    k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, nullptr, c->comm_a.p,
+                                                              c->cinfo.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
+                                                              c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self);
+  else
+    k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, c->weights.p, c->comm_a.p,
+                                                               nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
+                                                               nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self);
+  c->tm.kernel_launches++;
+  if (c->nghost) {
+    k_init_ghost_comm<<<grid_for(c->nghost, 256, nsm), 256, 0, s>>>(c->ghost_gid.p, (int)c->nghost, c->comm_a.p + lnv);
+    c->tm.kernel_launches++;
+  }
+
+  // high-degree vertices
+  const long long heavy_deg = (c->opt_force_heavy_deg > 0) ? std::min<long long>(c->opt_force_heavy_deg, kECap) : kECap;
+  c->nheavy = 0;
+  if (c->maxdeg > heavy_deg) {
+    TRY(c->heavy_list.ensure(lnv));
+    k_collect_heavy<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->rowptr.p, (unsigned int)heavy_deg, c->heavy_list.p, &d_sc->heavy_count);
+    c->tm.kernel_launches++;
+  }
+
+  // 1/(2m): MPI_Allreduce of the local degree sums (dspl.hpp:109-130)
+  if (c->nranks > 1) NK(g_nccl.AllReduce(&d_sc->total_weight, &d_sc->total_weight, 1, ncclDouble, ncclSum, c->comm, s));
+  CK(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  c->constant = 1.0 / h.total_weight;
+  const int has_self = h.has_self ? 1 : 0;
+  if (c->maxdeg > heavy_deg) {
+    c->nheavy = h.heavy_count;
+    std::vector<int32_t> hl(c->nheavy);
+    std::vector<uint32_t> rp;   // degrees of the heavy vertices
+    CK(cudaMemcpy(hl.data(), c->heavy_list.p, sizeof(int32_t) * c->nheavy, cudaMemcpyDeviceToHost));
+    std::sort(hl.begin(), hl.end());
+    CK(cudaMemcpy(c->heavy_list.p, hl.data(), sizeof(int32_t) * c->nheavy, cudaMemcpyHostToDevice));
+    std::vector<unsigned long long> off(c->nheavy + 1, 0);
+    for (long long i = 0; i < c->nheavy; i++) {
+      uint32_t r2[2];
+      CK(cudaMemcpy(r2, c->rowptr.p + hl[i], sizeof r2, cudaMemcpyDeviceToHost));
+      unsigned long long T = 64;
+      while (T < 2ULL * (r2[1] - r2[0])) T <<= 1;
+      off[i + 1] = off[i] + T;
+    }
+    TRY(c->heavy_off.ensure(c->nheavy + 1));
+    CK(cudaMemcpy(c->heavy_off.p, off.data(), sizeof(unsigned long long) * (c->nheavy + 1), cudaMemcpyHostToDevice));
+    TRY(c->hkeys.ensure(off[c->nheavy]));
+    if (c->unit) TRY(c->hvals_i.ensure(off[c->nheavy])); else TRY(c->hvals_d.ensure(off[c->nheavy]));
+  }
+  TRY(setup_peers(c, c->unit ? 1 : 0));
+  c->tm.unit_weight = c->unit ? 1 : 0;
+  c->scan_has_self = has_self;
+  c->scan_heavy_deg = (int)heavy_deg;
+  return 0;
+}
+
+
+// ---- ghost exchange: targetComm of the vertices peers ghost -> ghost tail of their community array.
+// The reference's gather + Isend/Irecv/Waitall (dspl.hpp:559-646) as one grouped NCCL all-to-all-v with
+// the run-constant counts from setup; the payload lands in place (no unpack, no remoteComm map).
+int exchange_ghosts(mvgpu_ctx *c, int32_t *comm) {
+  cudaStream_t s = c->stream;
+  if (c->nsend) {
+    k_pack_send<<<grid_for(c->nsend, 256, c->num_sms), 256, 0, s>>>(comm, c->send_lid.p, (int)c->nsend, c->send_buf.p);
+    c->tm.kernel_launches++;
+  }
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < c->nranks; r++) {
+    if (r == c->rank) continue;
+    if (c->scount[r]) NK(g_nccl.Send(c->send_buf.p + c->soff[r], c->scount[r], ncclInt32, r, c->comm, s));
+    if (c->rcount[r]) NK(g_nccl.Recv(comm + c->lnv + c->roff[r], c->rcount[r], ncclInt32, r, c->comm, s));
+  }
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+
+int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, double *mod_out) {
+  if (!c->have_graph) return fail("no graph uploaded");
+  if (c->nranks > 1 && !c->comm) return fail("mvgpu_comm_init has not been called");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  memset(&c->tm, 0, sizeof c->tm);
+  c->trace.clear();
+  size_t ev = 0;
+  cudaEvent_t e_begin = get_event(c, ev++), e_setup = get_event(c, ev++);
+  CK(cudaEventRecord(e_begin, s));
+  TRY(setup_run(c));
+  CK(cudaEventRecord(e_setup, s));
+
+  Scalars *d_sc = reinterpret_cast<Scalars *>(c->scratch.p);
+  int32_t *cur = c->comm_a.p, *tgt = c->comm_b.p;
+  ScanParams sp;
+  memset(&sp, 0, sizeof sp);
+  sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.base = c->base;
+  sp.rowptr = c->rowptr.p; sp.tails = c->tails.p; sp.weights = c->unit ? nullptr : c->weights.p;
+  sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
+  sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
+  sp.pt = c->pt;
+
+  struct HostMail { Acc acc; double red2[2]; unsigned long long tr2[2]; };
+  HostMail *mail = reinterpret_cast<HostMail *>(c->h_pin);
+  const size_t ev_iter0 = ev;
+  double prevMod = lower, currMod = -1.0;
+  int numIters = 0;
+  const int fold_grid = grid_for(c->lnv, 256, c->num_sms, 8);
+  for (;;) {                                                   // dspl.hpp:1338
+    if (numIters >= c->opt_max_iters) return fail("max_iters reached without convergence");
+    numIters++;
+    Acc *acc = c->acc.p + numIters;
+    sp.cur = cur; sp.tgt = tgt; sp.acc = acc;
+    cudaEvent_t e0 = get_event(c, ev++), e1 = get_event(c, ev++), e2 = get_event(c, ev++), e3 = get_event(c, ev++);
+    CK(cudaEventRecord(e0, s));
+    TRY(launch_scan(c, sp));
+    CK(cudaEventRecord(e1, s));
+    if (c->nranks > 1) {
+      // ghost values of the NEW assignment go into tgt's ghost tail; the all-reduce doubles as the
+      // "every scan has finished" barrier that must precede any fold (remote atomics / reads).
+      TRY(exchange_ghosts(c, tgt));
+      NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclSum, c->comm, s));
+    }
+    CK(cudaEventRecord(e2, s));
+    if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cinfo.p, c->upd.p, nullptr, nullptr, nullptr, acc);
+    else k_fold<false><<<fold_grid, 256, 0, s>>>((int)c->lnv, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
+    c->tm.kernel_launches++;
+    CK(cudaEventRecord(e3, s));
+    double e_xx, a2_x;
+    unsigned long long moved = 0, hash = 0;
+    if (c->nranks > 1) {
+      k_acc_to_double<<<1, 32, 0, s>>>(acc, c->unit ? 1 : 0, d_sc->red2);
+      c->tm.kernel_launches++;
+      NK(g_nccl.AllReduce(d_sc->red2, d_sc->red2, 2, ncclDouble, ncclSum, c->comm, s));   // dspl.hpp:441
+      CK(cudaMemcpyAsync(mail->red2, d_sc->red2, sizeof mail->red2, cudaMemcpyDeviceToHost, s));
+      if (c->opt_trace) {
+        k_trace_to_u64<<<1, 32, 0, s>>>(acc, d_sc->tr2);
+        c->tm.kernel_launches++;
+        NK(g_nccl.AllReduce(d_sc->tr2, d_sc->tr2, 2, ncclUint64, ncclSum, c->comm, s));
+        CK(cudaMemcpyAsync(mail->tr2, d_sc->tr2, sizeof mail->tr2, cudaMemcpyDeviceToHost, s));
+      }
+      CK(cudaStreamSynchronize(s));
+      e_xx = mail->red2[0]; a2_x = mail->red2[1];
+      moved = mail->tr2[0]; hash = mail->tr2[1];
+    } else {
+      CK(cudaMemcpyAsync(&mail->acc, acc, sizeof(Acc), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      e_xx = c->unit ? (double)mail->acc.le_u : mail->acc.le_d;
+      a2_x = c->unit ? (double)mail->acc.la2_u : mail->acc.la2_d;
+      moved = mail->acc.moved; hash = mail->acc.hash;
+    }
+    // dspl.hpp:447-448
+    const double cst = c->constant;
+    volatile double term1 = e_xx * cst;
+    volatile double term2a = a2_x * cst;
+    volatile double term2 = term2a * cst;
+    currMod = std::fabs(term1 - term2);
+    if (c->opt_trace) {
+      mvgpu_iter_trace t;
+      t.modularity = currMod; t.moved = (int64_t)moved; t.chash = hash;
+      c->trace.push_back(t);
+    }
+    if (currMod - prevMod < thresh) break;                     // dspl.hpp:1401-1402
+    prevMod = currMod;
+    if (prevMod < lower) prevMod = lower;                      // dspl.hpp:1404-1406
+    std::swap(cur, tgt);                                       // rotation (dspl.hpp:1408-1422) is a pointer swap
+  }
+  cudaEvent_t e_end = get_event(c, ev++);
+  CK(cudaEventRecord(e_end, s));
+  CK(cudaEventSynchronize(e_end));
+  c->d_final = cur;
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e_begin, e_end)); c->tm.total_s = ms * 1e-3;
+  CK(cudaEventElapsedTime(&ms, e_begin, e_setup)); c->tm.setup_s = ms * 1e-3;
+  for (int k = 0; k < numIters; k++) {
+    cudaEvent_t e0 = c->events[ev_iter0 + 4 * k], e1 = c->events[ev_iter0 + 4 * k + 1], e2 = c->events[ev_iter0 + 4 * k + 2],
+                e3 = c->events[ev_iter0 + 4 * k + 3];
+    CK(cudaEventElapsedTime(&ms, e0, e1)); c->tm.scan_s += ms * 1e-3;
+    CK(cudaEventElapsedTime(&ms, e1, e2)); c->tm.exchange_s += ms * 1e-3;
+    CK(cudaEventElapsedTime(&ms, e2, e3)); c->tm.fold_s += ms * 1e-3;
+  }
+  c->tm.iters = numIters;
+  c->tm.h2d_s = c->h2d_s;
+  *iters_out = numIters;                                       // dspl.hpp:1430
+  *mod_out = prevMod;                                          // dspl.hpp:1440
+  return 0;
+}
+
+__global__ void k_widen(const int32_t *in, long long n, long long *out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *mvgpu_last_error(void) { return g_err.c_str(); }
+
+int mvgpu_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { g_err = std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e); return -1; }
+  return n;
+}
+
+int mvgpu_create(mvgpu_ctx **out, int device, int rank, int nranks) {
+  if (!out) return fail("null ctx pointer");
+  if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) return fail("bad rank/nranks");
+  int n = 0;
+  CK(cudaGetDeviceCount(&n));
+  if (n < 1) return fail("no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail("device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(std::string("built for sm_100a, found ") + prop.name);
+  mvgpu_ctx *c = new mvgpu_ctx;
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  c->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMallocHost(&c->h_pin, 4096));
+  memset(&c->tm, 0, sizeof c->tm);
+  memset(&c->pt, 0, sizeof c->pt);
+  *out = c;
+  return 0;
+}
+
+int mvgpu_destroy(mvgpu_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
+  c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
+  c->cinfo.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
+  c->scratch.release(); c->cub_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
+  c->send_lid.release(); c->send_buf.release(); c->heavy_list.release(); c->hkeys.release(); c->hvals_i.release();
+  c->hvals_d.release(); c->heavy_off.release();
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int mvgpu_get_unique_id(void *id128) {
+  static_assert(sizeof(ncclUniqueId) == MVGPU_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  if (!mvnccl::load(g_nccl, g_err)) return 1;
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+int mvgpu_comm_init(mvgpu_ctx *c, const void *id128) {
+  if (!c) return fail("null ctx");
+  if (c->nranks == 1) return 0;
+  if (!mvnccl::load(g_nccl, g_err)) return 1;
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NK(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
+  return 0;
+}
+
+int mvgpu_upload_shard(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
+                       const int64_t *edge_indices, const void *edge_list) {
+  if (!c || !parts || !edge_indices || (lne && !edge_list)) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  TRY(set_graph(c, nv_global, parts, lnv, lne));
+  TRY(c->in_rowptr.ensure(lnv + 1));
+  TRY(c->in_edges.ensure(lne));
+  cudaEvent_t a = get_event(c, 0), b = get_event(c, 1);
+  CK(cudaEventRecord(a, c->stream));
+  CK(cudaMemcpyAsync(c->in_rowptr.p, edge_indices, sizeof(long long) * (lnv + 1), cudaMemcpyHostToDevice, c->stream));
+  if (lne) CK(cudaMemcpyAsync(c->in_edges.p, edge_list, sizeof(Edge16) * lne, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(b, c->stream));
+  CK(cudaEventSynchronize(b));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  c->h2d_s = ms * 1e-3;
+  c->d_rowptr64 = c->in_rowptr.p;
+  c->d_edges = c->in_edges.p;
+  return 0;
+}
+
+int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
+                              const int64_t *d_edge_indices, const void *d_edge_list) {
+  if (!c || !parts || !d_edge_indices || (lne && !d_edge_list)) return fail("null argument");
+  if (((uintptr_t)d_edge_list & 15) || ((uintptr_t)d_edge_indices & 7)) return fail("device arrays must be 16/8-byte aligned");
+  CK(cudaSetDevice(c->device));
+  TRY(set_graph(c, nv_global, parts, lnv, lne));
+  c->d_rowptr64 = reinterpret_cast<const long long *>(d_edge_indices);
+  c->d_edges = reinterpret_cast<const Edge16 *>(d_edge_list);
+  c->h2d_s = 0.0;
+  return 0;
+}
+
+int mvgpu_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters, double *modularity) {
+  if (!c || !iters || !modularity) return fail("null argument");
+  return run_louvain(c, lower, thresh, iters, modularity);
+}
+
+int mvgpu_get_communities_device(mvgpu_ctx *c, const int32_t **d_out) {
+  if (!c || !c->d_final) return fail("no result yet");
+  *d_out = c->d_final;
+  return 0;
+}
+
+int mvgpu_get_communities(mvgpu_ctx *c, int64_t *out) {
+  if (!c || !c->d_final) return fail("no result yet");
+  CK(cudaSetDevice(c->device));
+  if (c->lnv == 0) return 0;
+  DevBuf<long long> wide;
+  TRY(wide.ensure(c->lnv));
+  k_widen<<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>(c->d_final, c->lnv, wide.p);
+  CK(cudaMemcpyAsync(out, wide.p, sizeof(long long) * c->lnv, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  wide.release();
+  return 0;
+}
+
+int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
+  if (!c || !name) return fail("null argument");
+  const std::string n(name);
+  if (n == "trace") c->opt_trace = value != 0;
+  else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
+  else if (n == "force_weighted") c->opt_force_weighted = value != 0;
+  else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
+  else return fail("unknown option " + n);
+  return 0;
+}
+
+int mvgpu_get_trace(mvgpu_ctx *c, int max_entries, mvgpu_iter_trace *out, int *n) {
+  if (!c || !n) return fail("null argument");
+  const int k = std::min<int>(max_entries, (int)c->trace.size());
+  if (out && k > 0) memcpy(out, c->trace.data(), sizeof(mvgpu_iter_trace) * k);
+  *n = (int)c->trace.size();
+  return 0;
+}
+
+int mvgpu_get_timings(mvgpu_ctx *c, mvgpu_timings *out) {
+  if (!c || !out) return fail("null argument");
+  *out = c->tm;
+  return 0;
+}
+
+int mvgpu_get_constant(mvgpu_ctx *c, double *out) {
+  if (!c || !out) return fail("null argument");
+  *out = c->constant;
+  return 0;
+}
+
+int mvgpu_get_shard_info(mvgpu_ctx *c, int64_t *info6) {
+  if (!c || !info6) return fail("null argument");
+  info6[0] = c->lnv; info6[1] = c->lne; info6[2] = c->nghost; info6[3] = c->nsend; info6[4] = c->nheavy; info6[5] = c->maxdeg;
+  return 0;
+}
+
+int mvgpu_dist_louvain_method(int device, int64_t nv, int64_t ne_local, const int64_t *edge_indices, const void *edge_list,
+                              double lower, double thresh, int *iters, double *modularity, int64_t *comm_out) {
+  mvgpu_ctx *c = nullptr;
+  TRY(mvgpu_create(&c, device, 0, 1));
+  const int64_t parts[2] = {0, nv};
+  int rc = mvgpu_upload_shard(c, nv, parts, nv, ne_local, edge_indices, edge_list);
+  if (!rc) rc = mvgpu_louvain(c, lower, thresh, iters, modularity);
+  if (!rc && comm_out) rc = mvgpu_get_communities(c, comm_out);
+  const std::string keep = g_err;
+  mvgpu_destroy(c);
+  if (rc) g_err = keep;
+  return rc;
+}
+
+}  // extern "C"

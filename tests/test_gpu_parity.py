@@ -1,0 +1,154 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI,
+against the golden traces of the unmodified reference and against the C oracle on the same inputs.
+Bar: bit-exact community ids, iteration counts, moved counts and modularity for unit weights;
+|dQ| <= 1e-6 (BASELINE.json north_star tolerance) for non-unit weights."""
+import numpy as np
+import pytest
+
+from helpers import assert_trace_matches, case_graph
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from minivite_b200 import gpu as G
+    if G.device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the GPU box")
+    return G
+
+
+def run_single(G, parts, rowptr, edges, nv, **opts):
+    g = G.LouvainGPU(0, 0, 1)
+    try:
+        g.set_option("trace", 1)
+        for k, v in opts.items():
+            g.set_option(k, v)
+        g.upload(nv, parts, rowptr, edges)
+        mod, iters = g.louvain(-1.0, 1.0e-6)
+        return {"modularity": mod, "iters": iters, "trace": g.trace(), "comm": g.communities(),
+                "constant": g.constant(), "timings": g.timings(), "info": g.shard_info()}
+    finally:
+        g.close()
+
+
+def as_single(case):
+    """Merge a golden case's shards into one rank-0 shard (results are partition invariant for unit weights)."""
+    parts, rps, eds, keep = case_graph(case)
+    nv = int(parts[-1])
+    rowptr = np.concatenate([[0]] + [rp[1:] + off for rp, off in zip(rps, np.cumsum([0] + [len(e) for e in eds[:-1]]))])
+    edges = np.concatenate(eds) if len(eds) > 1 else eds[0]
+    return nv, np.array([0, nv], np.int64), rowptr.astype(np.int64), edges
+
+
+def is_weighted(name, case):
+    return name.endswith("_w") or "_w_" in name or "weighted" in name or case.get("unit_weight") is False
+
+
+def test_unit_weight_cases_bit_exact(gpu, golden):
+    from oracle import oracle as O
+    ran = 0
+    for name, case in golden.items():
+        if is_weighted(name, case):
+            continue
+        nv, parts, rowptr, edges = as_single(case)
+        res = run_single(gpu, parts, rowptr, edges, nv)
+        assert res["timings"]["unit_weight"] == 1, name
+        h = O.comm_hash(0, res["comm"])
+        assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], h, res["comm"])
+        assert repr(res["constant"]) == case["constant"], name
+        ran += 1
+    assert ran >= 20
+
+
+def test_weighted_cases(gpu, golden):
+    """fp64 path.  Sums are accumulated in edge order per vertex like the reference with 1 thread per rank;
+    community degrees are folded with atomics (any order), so the bar is the 1e-6 modularity tolerance,
+    and in practice the small cases are bit-identical."""
+    for name, case in golden.items():
+        if not is_weighted(name, case) or case["nranks"] != 1:
+            continue
+        nv, parts, rowptr, edges = as_single(case)
+        res = run_single(gpu, parts, rowptr, edges, nv)
+        assert res["timings"]["unit_weight"] == 0, name
+        assert abs(res["modularity"] - float(case["modularity"])) <= 1e-6, name
+        assert abs(res["iters"] - case["iters"]) <= 2, name
+
+
+def test_fp64_path_on_unit_graph_is_bit_exact(gpu, golden):
+    """force_weighted runs the general fp64 kernels on a unit-weight graph: every sum is an exact integer,
+    so the trace must again be bit-identical to the reference."""
+    case = golden["rgg_n16384_p1"]
+    nv, parts, rowptr, edges = as_single(case)
+    res = run_single(gpu, parts, rowptr, edges, nv, force_weighted=1)
+    assert res["timings"]["unit_weight"] == 0
+    assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+
+
+def test_high_degree_kernel(gpu, golden):
+    """force_heavy_deg routes vertices above a small degree through the high-degree (hash table) kernel."""
+    for name in ("hand_star41_p1", "rgg_n16384_p1", "hand_k66_p1"):
+        case = golden[name]
+        nv, parts, rowptr, edges = as_single(case)
+        res = run_single(gpu, parts, rowptr, edges, nv, force_heavy_deg=8)
+        assert res["info"]["nheavy"] > 0
+        assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
+    case = golden["rgg_n16384_p1"]
+    nv, parts, rowptr, edges = as_single(case)
+    res = run_single(gpu, parts, rowptr, edges, nv, force_heavy_deg=8, force_weighted=1)
+    assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+
+
+def test_against_oracle_on_fresh_graphs(gpu):
+    """Seeded inputs that are not in the golden file: CUDA path vs C oracle, sizes the oracle finishes in seconds."""
+    from minivite_b200 import hostgraph as hg
+    from oracle import oracle as O
+    for n, p, kw in [(8192, 1, {}), (262144, 1, {}), (131072, 4, {}), (65536, 1, {"random_edge_percent": 5.0}),
+                     (65536, 2, {"lcg": True})]:
+        ss = hg.generate_rgg(n, p, **kw)
+        parts = ss.shards[0].parts
+        ref = O.louvain(parts, [s.rowptr for s in ss.shards], [s.edges for s in ss.shards])
+        rowptr = np.concatenate([[0]] + [s.rowptr[1:] + off for s, off in
+                                         zip(ss.shards, np.cumsum([0] + [s.lne for s in ss.shards[:-1]]))])
+        edges = np.concatenate([s.edges for s in ss.shards])
+        res = run_single(gpu, np.array([0, n], np.int64), rowptr.astype(np.int64), edges, n)
+        assert res["iters"] == ref["iters"] and res["modularity"] == ref["modularity"], (n, p, kw)
+        assert np.array_equal(res["comm"], np.concatenate(ref["comm"]))
+        assert [int(x) for x in res["trace"]["chash"]] == [int(x) for x in ref["trace"]["chash"]]
+        assert [int(x) for x in res["trace"]["moved"]] == [int(x) for x in ref["trace"]["moved"]]
+
+
+def test_edge_cases(gpu):
+    from oracle import oracle as O
+    EDGE = np.dtype([("tail", "<i8"), ("weight", "<f8")])
+    # empty graph with vertices only
+    res = run_single(gpu, np.array([0, 5], np.int64), np.zeros(6, np.int64), np.zeros(0, EDGE), 5)
+    ref = O.louvain(np.array([0, 5], np.int64), [np.zeros(6, np.int64)], [np.zeros(0, EDGE)])
+    assert res["iters"] == ref["iters"]
+    assert (np.isnan(res["modularity"]) and np.isnan(ref["modularity"])) or res["modularity"] == ref["modularity"]
+    assert list(res["comm"]) == [0, 1, 2, 3, 4]
+    # bad input: tail out of range -> error, not a crash
+    from minivite_b200 import gpu as G
+    g = G.LouvainGPU(0, 0, 1)
+    ed = np.zeros(2, EDGE)
+    ed["tail"] = [1, 7]
+    ed["weight"] = 1.0
+    g.upload(2, np.array([0, 2], np.int64), np.array([0, 1, 2], np.int64), ed)
+    with pytest.raises(G.MvgpuError):
+        g.louvain()
+    g.close()
+
+
+def test_one_call_seam(gpu, golden):
+    """mvgpu_dist_louvain_method == distLouvainMethod(me=0, nprocs=1, g, ...) with host arrays."""
+    import ctypes
+    case = golden["rgg_n16384_p1"]
+    nv, parts, rowptr, edges = as_single(case)
+    L = gpu.lib()
+    iters = ctypes.c_int(0)
+    mod = ctypes.c_double(0)
+    comm = np.zeros(nv, np.int64)
+    rc = L.mvgpu_dist_louvain_method(0, nv, len(edges), rowptr.ctypes.data, edges.ctypes.data, -1.0, 1e-6,
+                                     ctypes.byref(iters), ctypes.byref(mod), comm.ctypes.data)
+    assert rc == 0, L.mvgpu_last_error()
+    assert iters.value == case["iters"] and mod.value == float(case["modularity"])

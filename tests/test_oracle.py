@@ -1,0 +1,64 @@
+"""CPU tests: the C restatement (oracle/louvain_oracle.c) and our RGG generator are pinned against the
+golden traces captured from the unmodified reference (tests/golden/ref_traces.json)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_trace_matches, case_graph
+from oracle import oracle as O
+
+
+def _names(golden_cases, prefix):
+    return sorted(k for k in golden_cases if k.startswith(prefix))
+
+
+def test_golden_file_has_all_kinds(golden):
+    kinds = {c["kind"] for c in golden.values()}
+    assert kinds == {"rgg", "file_rgg", "hand"}
+    assert golden["rgg_n16384_p1"]["modularity"] == "0.75671532450841406"   # SURVEY.md 8(c) known answer
+    assert golden["rgg_n16384_p1"]["final_chash"] == "5bf1e47053c42601"
+
+
+def test_oracle_matches_every_golden_case(golden):
+    for name, case in golden.items():
+        parts, rps, eds, _keep = case_graph(case)
+        assert sum(len(e) for e in eds) == case["ne"], name      # same graph as the reference built / read
+        res = O.louvain(parts, rps, eds)
+        comm = np.concatenate(res["comm"])
+        assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], res["chash_final"], comm)
+        assert repr(res["constant"]) == case["constant"], name
+
+
+def test_partition_invariance_unit_weights(golden):
+    """Same global graph on 1/2/4/8 shards -> identical traces."""
+    base = golden["file_rgg_n16384_s4_p1"]
+    for p in (2, 4, 8):
+        c = golden[f"file_rgg_n16384_s4_p{p}"]
+        assert c["trace"] == base["trace"] and c["modularity"] == base["modularity"]
+
+
+def test_first_iteration_rejected_returns_lower():
+    """dspl.hpp:1401-1440: if iteration 1 fails the test the function returns `lower` with iters == 1."""
+    # a graph without edges: modularity 0 - (-1) >= thresh, so use lower = 0.5 to force rejection
+    parts = np.array([0, 4], np.int64)
+    rp = np.array([0, 1, 2, 3, 4], np.int64)
+    ed = np.zeros(4, O.EDGE_DTYPE)
+    ed["tail"] = [1, 0, 3, 2]
+    ed["weight"] = 1.0
+    res = O.louvain(parts, [rp], [ed], lower=0.9)
+    assert res["iters"] == 1 and res["modularity"] == 0.9
+    assert list(res["comm"][0]) == [0, 1, 2, 3]
+
+
+@pytest.mark.skipif(not (O.have_reference() and os.path.isdir("/root/reference")),
+                    reason="live reference only in the build container")
+def test_oracle_against_live_reference(tmp_path):
+    from minivite_b200 import hostgraph as hg
+    ss = hg.generate_rgg(8192, 2)
+    path = str(tmp_path / "g.bin")
+    ss.write(path)
+    ref = O.run_reference(["-f", path], nranks=2, threads=1)
+    res = O.louvain(ss.shards[0].parts, [s.rowptr for s in ss.shards], [s.edges for s in ss.shards])
+    assert res["iters"] == ref["result"]["iters"] and res["modularity"] == ref["result"]["modularity"]
+    assert [int(t["chash"]) for t in res["trace"]] == [t["chash"] for t in ref["trace"]]
