@@ -1,0 +1,63 @@
+// Host replacement for the reference's distLouvainMethod (dspl.hpp:1280-1283): same parameter list,
+// same return value / `iters` semantics; the body marshals the Graph's arrays across the C ABI
+// (include/mvgpu.h) to the CUDA library instead of running the OpenMP/MPI loops.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "graph.hpp"
+#include "mvgpu.h"
+
+// What MPI_Comm carried in the reference: which GPU to use and (for nprocs > 1) the communicator id
+// every rank received from rank 0.
+struct GpuRankContext {
+  int device = 0;
+  unsigned char unique_id[MVGPU_UNIQUE_ID_BYTES] = {0};
+  bool trace = false;
+  std::vector<GraphElem> *comm_out = nullptr;     // final currComm of this rank (the reference drops it, dspl.hpp:1432-1438)
+  mvgpu_timings timings{};
+  std::vector<mvgpu_iter_trace> iter_trace;
+};
+
+[[noreturn]] inline void mv_abort(const std::string &where) {
+  // the reference's only error behaviour on this path is MPI_Abort(comm, -99) (main.cpp:90,251-276)
+  std::fprintf(stderr, "[miniVite_b200] %s: %s\n", where.c_str(), mvgpu_last_error());
+  std::exit(99);
+}
+
+// The 8 scratch parameters (ssz ... rvdata) are caller-owned out-params that only the reference's
+// exchangeVertexReqs filled (dspl.hpp:1106-1272); the ghost lists now live in device memory, so they
+// are left empty.
+inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph &dg, size_t &ssz, size_t &rsz,
+                                     std::vector<GraphElem> &ssizes, std::vector<GraphElem> &rsizes,
+                                     std::vector<GraphElem> &svdata, std::vector<GraphElem> &rvdata,
+                                     const GraphWeight lower, const GraphWeight thresh, int &iters,
+                                     GpuRankContext &rc) {
+  ssz = rsz = 0;
+  ssizes.clear(); rsizes.clear(); svdata.clear(); rvdata.clear();
+  mvgpu_ctx *ctx = nullptr;
+  if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
+  if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
+  if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
+  if (mvgpu_upload_shard(ctx, dg.get_nv(), dg.parts().data(), dg.get_lnv(), dg.get_lne(), dg.edge_indices_.data(),
+                         dg.edge_list_.data()))
+    mv_abort("mvgpu_upload_shard");
+  double mod = 0.0;
+  if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
+  mvgpu_get_timings(ctx, &rc.timings);
+  if (rc.trace) {
+    int n = 0;
+    mvgpu_get_trace(ctx, 0, nullptr, &n);
+    rc.iter_trace.resize(n);
+    if (n) mvgpu_get_trace(ctx, n, rc.iter_trace.data(), &n);
+  }
+  if (rc.comm_out) {
+    rc.comm_out->resize(dg.get_lnv());
+    if (mvgpu_get_communities(ctx, rc.comm_out->data())) mv_abort("mvgpu_get_communities");
+  }
+  mvgpu_destroy(ctx);
+  return mod;
+}

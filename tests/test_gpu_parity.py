@@ -87,11 +87,11 @@ def test_fp64_path_on_unit_graph_is_bit_exact(gpu, golden):
 
 def test_high_degree_kernel(gpu, golden):
     """force_heavy_deg routes vertices above a small degree through the high-degree (hash table) kernel."""
-    for name in ("hand_star41_p1", "rgg_n16384_p1", "hand_k66_p1"):
+    for name, thr in (("hand_star41_p1", 8), ("rgg_n16384_p1", 8), ("hand_k66_p1", 4), ("hand_loops_multi_p1", 2)):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
-        res = run_single(gpu, parts, rowptr, edges, nv, force_heavy_deg=8)
-        assert res["info"]["nheavy"] > 0
+        res = run_single(gpu, parts, rowptr, edges, nv, force_heavy_deg=thr)
+        assert res["info"]["nheavy"] > 0, (name, res["info"])
         assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
     case = golden["rgg_n16384_p1"]
     nv, parts, rowptr, edges = as_single(case)
