@@ -94,6 +94,8 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
 int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);
 int mvgpu_get_timings(mvgpu_ctx *ctx, mvgpu_timings *out);
+/* Device time (seconds) of the neighbour-scan launch(es) of each iteration of the last run; *n = #iterations. */
+int mvgpu_get_scan_times(mvgpu_ctx *ctx, int max_entries, double *out, int *n);
 /* 1/(2m), the reference's constantForSecondTerm (dspl.hpp:129), of the last run. */
 int mvgpu_get_constant(mvgpu_ctx *ctx, double *out);
 /* Shard statistics after upload/louvain: info[0]=lnv, [1]=lne, [2]=nghost, [3]=send list length,

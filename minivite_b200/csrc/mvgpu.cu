@@ -128,6 +128,7 @@ struct mvgpu_ctx {
   double constant = 0.0;
   int32_t *d_final = nullptr;          // currComm at exit (points into comm_a/comm_b)
   std::vector<mvgpu_iter_trace> trace;
+  std::vector<double> scan_times;
   mvgpu_timings tm;
   double h2d_s = 0.0;
   // pinned host mailbox
@@ -482,6 +483,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   cudaStream_t s = c->stream;
   memset(&c->tm, 0, sizeof c->tm);
   c->trace.clear();
+  c->scan_times.clear();
   size_t ev = 0;
   cudaEvent_t e_begin = get_event(c, ev++), e_setup = get_event(c, ev++);
   CK(cudaEventRecord(e_begin, s));
@@ -573,7 +575,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   for (int k = 0; k < numIters; k++) {
     cudaEvent_t e0 = c->events[ev_iter0 + 4 * k], e1 = c->events[ev_iter0 + 4 * k + 1], e2 = c->events[ev_iter0 + 4 * k + 2],
                 e3 = c->events[ev_iter0 + 4 * k + 3];
-    CK(cudaEventElapsedTime(&ms, e0, e1)); c->tm.scan_s += ms * 1e-3;
+    CK(cudaEventElapsedTime(&ms, e0, e1)); c->tm.scan_s += ms * 1e-3; c->scan_times.push_back(ms * 1e-3);
     CK(cudaEventElapsedTime(&ms, e1, e2)); c->tm.exchange_s += ms * 1e-3;
     CK(cudaEventElapsedTime(&ms, e2, e3)); c->tm.fold_s += ms * 1e-3;
   }
@@ -738,6 +740,14 @@ int mvgpu_get_trace(mvgpu_ctx *c, int max_entries, mvgpu_iter_trace *out, int *n
   const int k = std::min<int>(max_entries, (int)c->trace.size());
   if (out && k > 0) memcpy(out, c->trace.data(), sizeof(mvgpu_iter_trace) * k);
   *n = (int)c->trace.size();
+  return 0;
+}
+
+int mvgpu_get_scan_times(mvgpu_ctx *c, int max_entries, double *out, int *n) {
+  if (!c || !n) return fail("null argument");
+  const int k = std::min<int>(max_entries, (int)c->scan_times.size());
+  if (out && k > 0) memcpy(out, c->scan_times.data(), sizeof(double) * k);
+  *n = (int)c->scan_times.size();
   return 0;
 }
 

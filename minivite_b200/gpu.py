@@ -28,7 +28,7 @@ class Timings(ctypes.Structure):
 EXPORTS = ["mvgpu_last_error", "mvgpu_device_count", "mvgpu_create", "mvgpu_destroy", "mvgpu_get_unique_id",
            "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_louvain",
            "mvgpu_get_communities", "mvgpu_get_communities_device", "mvgpu_set_option", "mvgpu_get_trace",
-           "mvgpu_get_timings", "mvgpu_get_constant", "mvgpu_get_shard_info", "mvgpu_dist_louvain_method"]
+           "mvgpu_get_timings", "mvgpu_get_scan_times", "mvgpu_get_constant", "mvgpu_get_shard_info", "mvgpu_dist_louvain_method"]
 
 _lib = None
 
@@ -55,6 +55,7 @@ def lib():
         L.mvgpu_set_option.argtypes = [vp, ctypes.c_char_p, i64]
         L.mvgpu_get_trace.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
         L.mvgpu_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
+        L.mvgpu_get_scan_times.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
         L.mvgpu_get_constant.argtypes = [vp, ctypes.POINTER(dbl)]
         L.mvgpu_get_shard_info.argtypes = [vp, vp]
         L.mvgpu_dist_louvain_method.argtypes = [ci, i64, i64, vp, vp, dbl, dbl, ctypes.POINTER(ci),
@@ -145,6 +146,14 @@ class LouvainGPU:
         t = Timings()
         _ck(lib().mvgpu_get_timings(self._h, ctypes.byref(t)))
         return t.as_dict()
+
+    def scan_times(self):
+        n = ctypes.c_int(0)
+        _ck(lib().mvgpu_get_scan_times(self._h, 0, None, ctypes.byref(n)))
+        out = np.zeros(n.value, dtype=np.float64)
+        if n.value:
+            _ck(lib().mvgpu_get_scan_times(self._h, n.value, out.ctypes.data, ctypes.byref(n)))
+        return out
 
     def constant(self):
         v = ctypes.c_double(0)

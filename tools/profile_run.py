@@ -32,4 +32,6 @@ for r in range(runs):
     print(f"run {r}: mod={mod:.17g} iters={iters} total={tm['total_s']*1e3:.3f}ms setup={tm['setup_s']*1e3:.3f}ms "
           f"scan={tm['scan_s']*1e3:.3f}ms ({tm['scan_s']/iters*1e3:.3f} ms/iter) fold={tm['fold_s']*1e3:.3f}ms "
           f"edges/s={sh.lne*iters/tm['total_s']:.4g}", flush=True)
+    if r == runs - 1:
+        print("scan ms per iteration:", " ".join(f"{x*1e3:.2f}" for x in ctx.scan_times()), flush=True)
 ctx.close()
