@@ -10,12 +10,14 @@
 //   weights  double[lne]            only when some weight != 1.0
 //   cur/tgt  int32[lnv+nghost]      community (GLOBAL id) of every slot; ghosts are refreshed by the
 //                                   per-iteration exchange (dspl.hpp:559-688)
-//   unit-weight fast path (all weights 1, 2m < 2^31):
-//     cinfo  uint64[lnv]  = size<<32 | degree   (Comm{size,degree}, dspl.hpp:61-66, both exact integers)
-//     upd    uint64[lnv]  = packed two's-complement delta: ONE 64-bit atomic per community update
-//                           and fold is a single integer add (dspl.hpp:339-346 + 458-471)
+//   unit-weight fast path (all weights 1, 2m < 2^31): Comm{size,degree} (dspl.hpp:61-66) as exact integers, SoA:
+//     cdeg   uint32[lnv]  community degree: the only field the gain needs (4 B gather per candidate)
+//     csize  int32[lnv]   community size: read only for the singleton veto (dspl.hpp:224-225)
+//     upd    uint64[lnv]  = dsize*2^32 + ddeg packed two's-complement delta: ONE 64-bit atomic per community
+//                           update (dspl.hpp:339-346); fold decodes it (dspl.hpp:458-471)
 //   weighted path: cinfo_w {int64 size; double degree}[lnv], usize int64[lnv], udeg double[lnv], vdeg double[lnv]
-// With 32-bit ids the gathered arrays at 16M vertices are 64 MB (cur) + 128 MB (cinfo): largely L2 resident.
+// With 32-bit ids the randomly gathered arrays at 16M vertices are 64 MB (cur) + 64 MB (cdeg); `cur` gathers carry
+// an L2 evict_last policy and all streamed arrays evict_first so that the gather target stays L2 resident.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,7 +41,8 @@ struct Acc {                       // per-iteration accumulators (one record per
 struct PeerTable {                 // where community y lives: owner rank + that rank's arrays
   int nranks, rank;
   long long parts[kMaxRanks + 1];
-  const unsigned long long *cinfo[kMaxRanks];
+  const uint32_t *cdeg[kMaxRanks];
+  const int32_t *csize[kMaxRanks];
   unsigned long long *upd[kMaxRanks];
   const CommW *cinfo_w[kMaxRanks];
   long long *usize[kMaxRanks];
@@ -50,6 +53,7 @@ struct ScanParams {
   int lnv;
   int has_self;                    // any self loop in the shard (uniform branch)
   int heavy_deg;                   // degree > heavy_deg is left to the high-degree kernel (<= kECap)
+  int cache_policy;                // bit0: evict_last on cur gathers, bit1: evict_last on cdeg gathers, bit2: evict_first streams
   long long base;                  // global id of local vertex 0
   const uint32_t *rowptr;
   const int32_t *tails;
@@ -82,6 +86,33 @@ __device__ __forceinline__ unsigned long long vhash(long long gid, long long val
 // streaming (read-once) and read-only gathers
 __device__ __forceinline__ int ld_stream(const int32_t *p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+
+// L2 cache-policy descriptors (createpolicy) and loads/stores that carry them
+__device__ __forceinline__ unsigned long long make_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  unsigned long long pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_pol(const int32_t *p, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_pol(const uint32_t *p, unsigned long long pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_pol_stream(const int32_t *p, unsigned long long pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_pol(int32_t *p, int v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
 
 template <bool MULTI>
 __device__ __forceinline__ void locate(const PeerTable &pt, long long base, int y, int &owner, long long &idx) {
@@ -218,9 +249,8 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
               if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
             s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
           }
-          const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[owner] : p.pt.cinfo[0]) + idx);
-          cc_size = (long long)(ci >> 32);
-          cc_deg = (double)(uint32_t)ci;
+          cc_size = (long long)__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
+          cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
           vdeg = (double)d;
           const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
           eix = (double)(cnt0 - sl);
@@ -254,9 +284,8 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
           locate<MULTI>(p.pt, p.base, y, yo, yi);
           double ay, eiy; long long ysize;
           if (UNIT) {
-            const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[yo] : p.pt.cinfo[0]) + yi);
-            ysize = (long long)(ci >> 32);
-            ay = (double)(uint32_t)ci;
+            ysize = (long long)__ldg((MULTI ? p.pt.csize[yo] : p.pt.csize[0]) + yi);
+            ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
             eiy = (double)s_cnt[o0 + m];
           } else {
             const double2 raw = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi));
@@ -318,6 +347,241 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Unit-weight scan kernel, second generation.  Same tile/sub-range structure and phase A as k_scan;
+// phase B keeps a vertex's (<= kFastDeg) staged neighbour communities in REGISTERS:
+//   * Batcher odd-even merge sorting network (63 compare-exchanges, no divergence, no shared-memory
+//     traffic) -> equal communities become adjacent; run lengths are the per-community edge counts
+//     (counter[] of dspl.hpp:262-270 for unit weights);
+//   * the <= 16 degree gathers of the distinct neighbour communities are issued back to back
+//     (memory-level parallelism instead of a dependent chain), then the gains (dspl.hpp:212) and the
+//     (gain desc, id asc) selection (dspl.hpp:214-219) run on registers;
+//   * community sizes are only read when the singleton veto (dspl.hpp:224-225) can fire.
+// Vertices with more than kFastDeg staged neighbours (5.6% on the benchmark RGG) are queued in shared
+// memory and handled afterwards by the generic in-place reduction, densely packed into few warps.
+// Cache policy: `cur` gathers evict_last, streamed tails / rowptr / target writes evict_first.
+// ----------------------------------------------------------------------------------------------
+constexpr int kFastDeg = 16;
+
+__device__ __forceinline__ void cmpx(int &a, int &b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+template <bool MULTI>
+__device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
+  int bo, co; long long bi, ci;
+  locate<MULTI>(p.pt, p.base, best, bo, bi);
+  locate<MULTI>(p.pt, p.base, cc, co, ci);
+  atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)d));
+  atomicAdd((MULTI ? p.pt.upd[co] : p.pt.upd[0]) + ci, pack_delta(-1, -(long long)d));
+}
+
+// generic in-place reduction of one vertex's staged segment (any degree <= kECap), unit weights
+template <bool MULTI>
+__device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_comm, int32_t *s_cnt, int o0, int d, int v,
+                                                int cc, unsigned long long &acc_le) {
+  int nd = 0, cnt0 = 0;
+  for (int k = 0; k < d; k++) {
+    const int ck = s_comm[o0 + k];
+    if (ck == cc) { cnt0++; continue; }
+    if (ck < 0) continue;
+    int c = 1;
+    for (int j = k + 1; j < d; j++)
+      if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
+    s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
+  }
+  int owner; long long idx;
+  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  const double cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+  const double vdeg = (double)d;
+  const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
+  const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
+  acc_le += (unsigned long long)cnt0;
+  double bg = 0.0;
+  int best = cc;
+  for (int m = 0; m < nd; m++) {
+    const int y = s_comm[o0 + m];
+    int yo; long long yi;
+    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    const double ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+    const double g = gain_of((double)s_cnt[o0 + m], eix, vdeg, ay, ax, p.constant);
+    if (better(g, y, bg, best)) { bg = g; best = y; }
+  }
+  if (best > cc) {                                                           // dspl.hpp:224-225
+    int bo; long long bi;
+    locate<MULTI>(p.pt, p.base, best, bo, bi);
+    if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 && __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
+      best = cc;
+  }
+  return best;
+}
+
+template <bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);     // kECap staged neighbour communities
+  int32_t *s_cnt = s_comm + kECap;                             // kECap counts (slow path only)
+  __shared__ int s_next, s_nslow, s_end, s_skip;
+  __shared__ uint32_t s_e0;
+  __shared__ int s_slow[kTileV];
+  __shared__ unsigned long long s_red[3][kTileV / 32];
+
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileV;
+  const int v1 = min(p.lnv, v0 + kTileV);
+  const int v = v0 + tid;
+  const unsigned long long pol_cur = make_policy((p.cache_policy & 1) ? 1 : 0);
+  const unsigned long long pol_deg = make_policy((p.cache_policy & 2) ? 1 : 0);
+  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
+  uint32_t r0 = 0, r1 = 0;
+  if (v < v1) { r0 = ld_pol(p.rowptr + v, pol_str); r1 = ld_pol(p.rowptr + v + 1, pol_str); }
+  const uint32_t deg = r1 - r0;
+  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
+  unsigned long long acc_le = 0, acc_moved = 0, acc_hash = 0;
+
+  int start = v0;
+  while (start < v1) {
+    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
+    __syncthreads();
+    if (s_skip) { start++; __syncthreads(); continue; }
+    const uint32_t E0 = s_e0;
+    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
+    __syncthreads();
+    const int end = s_end;
+    if (tid == end - 1 - v0) s_next = (int)r1;
+    __syncthreads();
+    const int ne = (int)((uint32_t)s_next - E0);
+
+    // ---- phase A: coalesced stream of tails, gather cur[tail] (evict_last), stage in shared memory
+    {
+      const int32_t *tl = p.tails + E0;
+      int i = tid;
+      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
+        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
+                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
+        const int c0 = ld_pol(p.cur + t0, pol_cur), c1 = ld_pol(p.cur + t1, pol_cur), c2 = ld_pol(p.cur + t2, pol_cur),
+                  c3 = ld_pol(p.cur + t3, pol_cur);
+        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      }
+      for (; i < ne; i += kTileV) s_comm[i] = ld_pol(p.cur + ld_pol_stream(tl + i, pol_str), pol_cur);
+    }
+    __syncthreads();
+
+    // ---- phase B (fast path): registers + sorting network
+    const bool mine = (v >= start && v < end);
+    int cc = 0, best = 0;
+    if (mine) {
+      cc = ld_pol(p.cur + v, pol_cur);
+      best = cc;
+      const int d = (int)deg;
+      if (d > kFastDeg) s_slow[atomicAdd(&s_nslow, 1)] = tid;
+      else if (d != 0) {
+        const int o0 = (int)(r0 - E0);
+        int a[kFastDeg];
+#pragma unroll
+        for (int k = 0; k < kFastDeg; k++) a[k] = (k < d) ? s_comm[o0 + k] : 0x7fffffff;
+        // Batcher odd-even merge sort for 16 keys, 63 compare-exchanges, written out (generated; verified with the
+        // 0/1 principle) so that every index is a literal and the keys stay in registers
+        cmpx(a[0], a[1]); cmpx(a[2], a[3]); cmpx(a[4], a[5]); cmpx(a[6], a[7]); cmpx(a[8], a[9]); cmpx(a[10], a[11]);
+        cmpx(a[12], a[13]); cmpx(a[14], a[15]); cmpx(a[0], a[2]); cmpx(a[1], a[3]); cmpx(a[4], a[6]); cmpx(a[5], a[7]);
+        cmpx(a[8], a[10]); cmpx(a[9], a[11]); cmpx(a[12], a[14]); cmpx(a[13], a[15]); cmpx(a[1], a[2]); cmpx(a[5], a[6]);
+        cmpx(a[9], a[10]); cmpx(a[13], a[14]); cmpx(a[0], a[4]); cmpx(a[1], a[5]); cmpx(a[2], a[6]); cmpx(a[3], a[7]);
+        cmpx(a[8], a[12]); cmpx(a[9], a[13]); cmpx(a[10], a[14]); cmpx(a[11], a[15]); cmpx(a[2], a[4]); cmpx(a[3], a[5]);
+        cmpx(a[10], a[12]); cmpx(a[11], a[13]); cmpx(a[1], a[2]); cmpx(a[3], a[4]); cmpx(a[5], a[6]); cmpx(a[9], a[10]);
+        cmpx(a[11], a[12]); cmpx(a[13], a[14]); cmpx(a[0], a[8]); cmpx(a[1], a[9]); cmpx(a[2], a[10]); cmpx(a[3], a[11]);
+        cmpx(a[4], a[12]); cmpx(a[5], a[13]); cmpx(a[6], a[14]); cmpx(a[7], a[15]); cmpx(a[4], a[8]); cmpx(a[5], a[9]);
+        cmpx(a[6], a[10]); cmpx(a[7], a[11]); cmpx(a[2], a[4]); cmpx(a[3], a[5]); cmpx(a[6], a[8]); cmpx(a[7], a[9]);
+        cmpx(a[10], a[12]); cmpx(a[11], a[13]); cmpx(a[1], a[2]); cmpx(a[3], a[4]); cmpx(a[5], a[6]); cmpx(a[7], a[8]);
+        cmpx(a[9], a[10]); cmpx(a[11], a[12]); cmpx(a[13], a[14]);
+        // run lengths: rl[k] = length of the run that ends at k (0 if k is not a run end)
+        int rl[kFastDeg];
+        int run = 0, cnt0 = 0;
+#pragma unroll
+        for (int k = 0; k < kFastDeg; k++) {
+          run++;
+          const bool endrun = (k == kFastDeg - 1) || (a[k] != a[k + 1]);
+          int r = endrun ? run : 0;
+          if (endrun) run = 0;
+          if (a[k] == 0x7fffffff) r = 0;                   // padding
+          if (a[k] == cc) { cnt0 += r; r = 0; }            // own community: counter[0]
+          rl[k] = r;
+        }
+        // degree gathers of the distinct neighbour communities, all in flight together
+        uint32_t dg[kFastDeg];
+#pragma unroll
+        for (int k = 0; k < kFastDeg; k++) {
+          dg[k] = 0;
+          if (rl[k]) {
+            int yo; long long yi;
+            locate<MULTI>(p.pt, p.base, a[k], yo, yi);
+            dg[k] = ld_pol((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi, pol_deg);
+          }
+        }
+        int owner; long long idx;
+        locate<MULTI>(p.pt, p.base, cc, owner, idx);
+        const double cc_deg = (double)ld_pol((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx, pol_deg);
+        const double vdeg = (double)d;
+        const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
+        const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
+        acc_le += (unsigned long long)cnt0;
+        double bg = 0.0;
+#pragma unroll
+        for (int k = 0; k < kFastDeg; k++) {
+          if (rl[k]) {
+            const double g = gain_of((double)rl[k], eix, vdeg, (double)dg[k], ax, p.constant);
+            if (better(g, a[k], bg, best)) { bg = g; best = a[k]; }
+          }
+        }
+        if (best > cc) {                                                     // singleton veto, dspl.hpp:224-225
+          int bo; long long bi;
+          locate<MULTI>(p.pt, p.base, best, bo, bi);
+          if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 &&
+              __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
+            best = cc;
+        }
+        if (best != cc) push_move_unit<MULTI>(p, cc, best, d);               // dspl.hpp:331-399
+      }
+      if (d <= kFastDeg) {
+        st_pol(p.tgt + v, best, pol_str);                                    // dspl.hpp:404
+        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(p.base + v, best); }
+      }
+    }
+    __syncthreads();
+    // ---- phase B (slow path): queued larger vertices, one thread each, packed into the first warps
+    const int nslow = s_nslow;
+    for (int q = tid; q < nslow; q += kTileV) {
+      const int t = s_slow[q];
+      const int sv = v0 + t;
+      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
+      const int scc = __ldg(p.cur + sv);
+      const int sd = (int)(sr1 - sr0);
+      const int sbest = slow_vertex_unit<MULTI>(p, s_comm, s_cnt, (int)(sr0 - E0), sd, sv, scc, acc_le);
+      if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
+      p.tgt[sv] = sbest;
+      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(p.base + sv, sbest); }
+    }
+    start = end;
+    __syncthreads();
+  }
+
+  const int lane = tid & 31, wid = tid >> 5;
+  { const unsigned long long s = warp_sum(acc_le); if (lane == 0) s_red[0][wid] = s; }
+  if (TRACE) {
+    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
+    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
+    if (s) atomicAdd(&p.acc->le_u, s);
+    if (TRACE) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
+      atomicAdd(&p.acc->moved, a);
+      atomicAdd(&p.acc->hash, b);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // High-degree vertices (degree > heavy_deg): one CTA per vertex, open-addressing table in HBM
 // scratch (2x degree entries) keyed by neighbour community; same decision rule.  Weighted sums are
 // accumulated with fp64 atomics here (order not fixed: weighted parity is tolerance-based anyway).
@@ -361,8 +625,8 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
   locate<MULTI>(p.pt, p.base, cc, owner, idx);
   double cc_deg, vdeg, sl; long long cc_size;
   if (UNIT) {
-    const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[owner] : p.pt.cinfo[0]) + idx);
-    cc_size = (long long)(ci >> 32); cc_deg = (double)(uint32_t)ci;
+    cc_size = (long long)__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
+    cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
     vdeg = (double)(e1 - e0);
     sl = p.has_self ? (double)p.self_i[v] : 0.0;
   } else {
@@ -381,8 +645,8 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     locate<MULTI>(p.pt, p.base, y, yo, yi);
     double ay, eiy; long long ysz;
     if (UNIT) {
-      const unsigned long long ci = __ldg((MULTI ? p.pt.cinfo[yo] : p.pt.cinfo[0]) + yi);
-      ysz = (long long)(ci >> 32); ay = (double)(uint32_t)ci; eiy = (double)vi[i];
+      ysz = (long long)__ldg((MULTI ? p.pt.csize[yo] : p.pt.csize[0]) + yi);
+      ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi); eiy = (double)vi[i];
     } else {
       const CommW cw = (MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0])[yi];
       ysz = cw.size; ay = cw.degree; eiy = vd[i];
@@ -432,17 +696,23 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
 // and accumulate sum(degree^2) for the modularity (dspl.hpp:458-471, 978-1103, 473-486, 432).
 // ----------------------------------------------------------------------------------------------
 template <bool UNIT>
-__global__ void __launch_bounds__(256) k_fold(int lnv, unsigned long long *cinfo, unsigned long long *upd, CommW *cinfo_w,
+__global__ void __launch_bounds__(256) k_fold(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, CommW *cinfo_w,
                                               long long *usize, double *udeg, Acc *acc) {
   unsigned long long a2u = 0;
   double a2d = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lnv; i += gridDim.x * blockDim.x) {
     if (UNIT) {
-      unsigned long long c = cinfo[i];
+      uint32_t dg = cdeg[i];
       const unsigned long long u = upd[i];
-      if (u) { c += u; cinfo[i] = c; upd[i] = 0; }
-      const unsigned long long d = (uint32_t)c;
-      a2u += d * d;
+      if (u) {                                   // u = dsize*2^32 + ddeg (exact two's-complement sum of the deltas)
+        const int ddeg = (int)(uint32_t)u;
+        const int dsize = (int)(((long long)u - (long long)ddeg) >> 32);
+        dg += (uint32_t)ddeg;
+        cdeg[i] = dg;
+        if (dsize) csize[i] += dsize;
+        upd[i] = 0;
+      }
+      a2u += (unsigned long long)dg * dg;
     } else {
       CommW c = cinfo_w[i];
       const long long us = usize[i];
@@ -551,7 +821,7 @@ __global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int
 // distSumVertexDegree + distInitComm + self-loop weights (dspl.hpp:82-107, 132-149, 247-248/285)
 template <bool UNIT>
 __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, const uint32_t *rowptr, const int32_t *tails,
-                                                     const double *weights, int32_t *cur, unsigned long long *cinfo,
+                                                     const double *weights, int32_t *cur, uint32_t *cdeg, int32_t *csize,
                                                      unsigned long long *upd, CommW *cinfo_w, long long *usize, double *udeg,
                                                      double *vdeg, int32_t *self_i, double *self_d, double *total_weight,
                                                      unsigned int *has_self) {
@@ -565,7 +835,8 @@ __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, co
       for (uint32_t e = e0; e < e1; e++) sl += (tails[e] == v);
       self_i[v] = sl;
       any_self |= (sl != 0);
-      cinfo[v] = (1ULL << 32) | (unsigned long long)(e1 - e0);
+      cdeg[v] = e1 - e0;
+      csize[v] = 1;
       upd[v] = 0;
       tw_sum += (double)(e1 - e0);
     } else {

@@ -66,8 +66,8 @@ struct DevBuf {              // grow-only device buffer (allocations are cached 
 };
 
 struct PeerBlob {            // what every rank publishes about its community arrays
-  cudaIpcMemHandle_t h[5];
-  unsigned long long raw[5];
+  cudaIpcMemHandle_t h[6];
+  unsigned long long raw[6];
   int pid, device, unit, pad;
 };
 
@@ -97,7 +97,9 @@ struct mvgpu_ctx {
   DevBuf<double> self_d, vdeg;
   // state
   DevBuf<int32_t> comm_a, comm_b;
-  DevBuf<unsigned long long> cinfo, upd;
+  DevBuf<uint32_t> cdeg;
+  DevBuf<int32_t> csize;
+  DevBuf<unsigned long long> upd;
   DevBuf<CommW> cinfo_w;
   DevBuf<long long> usize;
   DevBuf<double> udeg;
@@ -121,7 +123,7 @@ struct mvgpu_ctx {
   bool peers_ready = false;
   int peers_unit = -1;
   // options
-  int opt_trace = 0, opt_force_weighted = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 1, opt_cache_policy = 5;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -192,7 +194,7 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   pt.nranks = c->nranks; pt.rank = c->rank;
   for (int r = 0; r <= c->nranks; r++) pt.parts[r] = c->parts[r];
   if (c->nranks == 1) {
-    pt.cinfo[0] = c->cinfo.p; pt.upd[0] = c->upd.p; pt.cinfo_w[0] = c->cinfo_w.p; pt.usize[0] = c->usize.p; pt.udeg[0] = c->udeg.p;
+    pt.cdeg[0] = c->cdeg.p; pt.csize[0] = c->csize.p; pt.upd[0] = c->upd.p; pt.cinfo_w[0] = c->cinfo_w.p; pt.usize[0] = c->usize.p; pt.udeg[0] = c->udeg.p;
     return 0;
   }
   if (c->peers_ready && c->peers_unit == unit) return 0;
@@ -200,10 +202,10 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   c->ipc_opened.clear();
   PeerBlob mine;
   memset(&mine, 0, sizeof mine);
-  void *ptrs[5] = {unit ? (void *)c->cinfo.p : nullptr, unit ? (void *)c->upd.p : nullptr,
+  void *ptrs[6] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
                    unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
                    unit ? nullptr : (void *)c->udeg.p};
-  for (int k = 0; k < 5; k++) {
+  for (int k = 0; k < 6; k++) {
     mine.raw[k] = (unsigned long long)ptrs[k];
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
   }
@@ -217,9 +219,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   CK(cudaStreamSynchronize(c->stream));
   d_all.release();
   for (int r = 0; r < c->nranks; r++) {
-    void *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (all[r].unit != unit) return fail("ranks disagree on the unit-weight path");
-    if (r == c->rank) { for (int k = 0; k < 5; k++) q[k] = ptrs[k]; }
+    if (r == c->rank) { for (int k = 0; k < 6; k++) q[k] = ptrs[k]; }
     else if (all[r].pid == mine.pid) {           // same process (threads): plain UVA pointers + peer access
       int can = 0;
       CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
@@ -227,16 +229,16 @@ int setup_peers(mvgpu_ctx *c, int unit) {
       cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
       cudaGetLastError();
-      for (int k = 0; k < 5; k++) q[k] = (void *)all[r].raw[k];
+      for (int k = 0; k < 6; k++) q[k] = (void *)all[r].raw[k];
     } else {
-      for (int k = 0; k < 5; k++)
+      for (int k = 0; k < 6; k++)
         if (all[r].raw[k]) {
           CK(cudaIpcOpenMemHandle(&q[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess));
           c->ipc_opened.push_back(q[k]);
         }
     }
-    pt.cinfo[r] = (const unsigned long long *)q[0]; pt.upd[r] = (unsigned long long *)q[1];
-    pt.cinfo_w[r] = (const CommW *)q[2]; pt.usize[r] = (long long *)q[3]; pt.udeg[r] = (double *)q[4];
+    pt.cdeg[r] = (const uint32_t *)q[0]; pt.csize[r] = (const int32_t *)q[1]; pt.upd[r] = (unsigned long long *)q[2];
+    pt.cinfo_w[r] = (const CommW *)q[3]; pt.usize[r] = (long long *)q[4]; pt.udeg[r] = (double *)q[5];
   }
   c->peers_ready = true;
   c->peers_unit = unit;
@@ -249,11 +251,13 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(k_scan<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (UNIT) CK(cudaFuncSetAttribute(k_scan_fast<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
   if (tiles > 0) {
-    k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    if (UNIT && c->opt_scan_variant == 1) k_scan_fast<MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    else k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   }
   if (c->nheavy > 0) {
@@ -395,18 +399,18 @@ int setup_run(mvgpu_ctx *c) {
   const long long nslots = lnv + c->nghost;
   TRY(c->comm_a.ensure(nslots));
   TRY(c->comm_b.ensure(nslots));
-  if (c->unit) { TRY(c->cinfo.ensure(lnv)); TRY(c->upd.ensure(lnv)); TRY(c->self_i.ensure(lnv)); }
+  if (c->unit) { TRY(c->cdeg.ensure(lnv)); TRY(c->csize.ensure(lnv)); TRY(c->upd.ensure(lnv)); TRY(c->self_i.ensure(lnv)); }
   else { TRY(c->cinfo_w.ensure(lnv)); TRY(c->usize.ensure(lnv)); TRY(c->udeg.ensure(lnv)); TRY(c->vdeg.ensure(lnv)); TRY(c->self_d.ensure(lnv)); }
   TRY(c->acc.ensure((size_t)c->opt_max_iters + 2));
   CK(cudaMemsetAsync(c->acc.p, 0, sizeof(Acc) * ((size_t)c->opt_max_iters + 2), s));
 
   if (c->unit)
     k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, nullptr, c->comm_a.p,
-                                                              c->cinfo.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
+                                                              c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
                                                               c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self);
   else
     k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, c->weights.p, c->comm_a.p,
-                                                               nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
+                                                               nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
                                                                nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self);
   c->tm.kernel_launches++;
   if (c->nghost) {
@@ -495,6 +499,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   ScanParams sp;
   memset(&sp, 0, sizeof sp);
   sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.base = c->base;
+  sp.cache_policy = c->opt_cache_policy;
   sp.rowptr = c->rowptr.p; sp.tails = c->tails.p; sp.weights = c->unit ? nullptr : c->weights.p;
   sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
   sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
@@ -522,8 +527,8 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclSum, c->comm, s));
     }
     CK(cudaEventRecord(e2, s));
-    if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cinfo.p, c->upd.p, nullptr, nullptr, nullptr, acc);
-    else k_fold<false><<<fold_grid, 256, 0, s>>>((int)c->lnv, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
+    if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, acc);
+    else k_fold<false><<<fold_grid, 256, 0, s>>>((int)c->lnv, nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
     c->tm.kernel_launches++;
     CK(cudaEventRecord(e3, s));
     double e_xx, a2_x;
@@ -637,7 +642,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
-  c->cinfo.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
+  c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
   c->scratch.release(); c->cub_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
   c->send_lid.release(); c->send_buf.release(); c->heavy_list.release(); c->hkeys.release(); c->hvals_i.release();
   c->hvals_d.release(); c->heavy_off.release();
@@ -731,6 +736,8 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
   else if (n == "force_weighted") c->opt_force_weighted = value != 0;
   else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
+  else if (n == "scan_variant") c->opt_scan_variant = (int)value;
+  else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else return fail("unknown option " + n);
   return 0;
 }

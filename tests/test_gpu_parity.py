@@ -163,3 +163,37 @@ def test_one_call_seam(gpu, golden):
                                      ctypes.byref(iters), ctypes.byref(mod), comm.ctypes.data)
     assert rc == 0, L.mvgpu_last_error()
     assert iters.value == case["iters"] and mod.value == float(case["modularity"])
+
+
+def test_scan_variants_agree(gpu, golden):
+    """generic kernel (scan_variant=0) and register/sorting-network kernel (1) give the same golden trace;
+    cache-policy settings never change results."""
+    case = golden["rgg_n65536_p1"]
+    nv, parts, rowptr, edges = as_single(case)
+    for opts in ({"scan_variant": 0}, {"scan_variant": 1}, {"scan_variant": 1, "cache_policy": 0},
+                 {"scan_variant": 1, "cache_policy": 7}):
+        res = run_single(gpu, parts, rowptr, edges, nv, **opts)
+        assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+
+
+def test_full_size_config2_matches_reference_trace(gpu):
+    """BASELINE.json configs[1]: RGG -n 16777216 on one GPU.  The golden trace was produced by the unmodified
+    reference (oracle/_ref, 128 host threads, tools/make_fullsize_golden.py) on the same graph file."""
+    import json
+    import os
+    from minivite_b200 import hostgraph as hg
+    from oracle import oracle as O
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_full_16777216_p1.json")))
+    ss = hg.generate_rgg(gold["nv"], 1)
+    sh = ss.shards[0]
+    assert sh.lne == gold["ne"]
+    res = run_single(gpu, sh.parts, sh.rowptr, sh.edges, gold["nv"])
+    assert res["iters"] == gold["iters"]
+    assert repr(res["modularity"]) == repr(float(gold["modularity"]))
+    for t, g in zip(res["trace"], gold["trace"]):
+        assert float(t["modularity"]) == float(g["modularity"]) and int(t["moved"]) == g["moved"]
+        assert int(t["chash"]) == int(g["chash"], 16)
+    assert "%016x" % O.comm_hash(0, res["comm"]) == gold["final_chash"]
+    # size-independent properties: community ids are vertex ids of members' lineage, sizes add up
+    comm = res["comm"]
+    assert comm.min() >= 0 and comm.max() < gold["nv"]
