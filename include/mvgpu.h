@@ -50,6 +50,9 @@ typedef struct {
   int64_t kernel_launches; /* all kernels of this library launched inside total_s */
   int32_t iters;
   int32_t unit_weight;   /* 1 if the integer fast path ran (all weights 1.0, 2m < 2^31) */
+  double reorder_s;      /* part of setup_s spent on the locality renumbering (0 when it did not run) */
+  int32_t reordered;     /* 1 if this rank's vertices were renumbered for locality */
+  int32_t pad_;
 } mvgpu_timings;
 
 const char *mvgpu_last_error(void);
@@ -93,7 +96,9 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
  * "scan_variant" (1 = register/sorting-network unit kernel (default), 0 = generic kernel),
  * "cache_policy" (bit0 evict_last on community gathers, bit1 evict_last on degree gathers, bit2 evict_first on
- * streamed arrays; default 5). */
+ * streamed arrays; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
+ * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
+ * vertices per BFS region of the renumbering, default 4096). */
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
 int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);
 int mvgpu_get_timings(mvgpu_ctx *ctx, mvgpu_timings *out);

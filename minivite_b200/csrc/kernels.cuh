@@ -19,6 +19,7 @@
 // With 32-bit ids the randomly gathered arrays at 16M vertices are 64 MB (cur) + 64 MB (cdeg); `cur` gathers carry
 // an L2 evict_last policy and all streamed arrays evict_first so that the gather target stays L2 resident.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -47,12 +48,14 @@ struct PeerTable {                 // where community y lives: owner rank + that
   const CommW *cinfo_w[kMaxRanks];
   long long *usize[kMaxRanks];
   double *udeg[kMaxRanks];
+  const int32_t *lab[kMaxRanks];   // label (original global vertex id) of every internal vertex/community id
 };
 
 struct ScanParams {
   int lnv;
   int has_self;                    // any self loop in the shard (uniform branch)
   int heavy_deg;                   // degree > heavy_deg is left to the high-degree kernel (<= kECap)
+  int relabel;                     // vertices were renumbered for locality: ids are internal, tie-breaks use labels
   int cache_policy;                // bit0: evict_last on cur gathers, bit1: evict_last on cdeg gathers, bit2: evict_first streams
   long long base;                  // global id of local vertex 0
   const uint32_t *rowptr;
@@ -139,6 +142,36 @@ __device__ __forceinline__ double gain_of(double eiy, double eix, double vdeg, d
 // (gain, id) ordering of dspl.hpp:214-215: larger gain wins; equal non-zero gains -> smaller id.
 __device__ __forceinline__ bool better(double g, int y, double bg, int by) {
   return (g > bg) || ((g == bg) && (g != 0.0) && (y < by));
+}
+
+// Locality renumbering keeps the reference's semantics by comparing LABELS (original global vertex ids of
+// the community founders) wherever the reference compares community ids (dspl.hpp:215, 224).
+constexpr int kNoLabel = (int)0x80000000;
+template <bool MULTI>
+__device__ __forceinline__ int label_of(const ScanParams &p, int c) {
+  if (!p.relabel) return c;
+  int o; long long i;
+  locate<MULTI>(p.pt, p.base, c, o, i);
+  return __ldg((MULTI ? p.pt.lab[o] : p.pt.lab[0]) + i);
+}
+// better() with lazily fetched labels; lby caches the label of the current best (kNoLabel = not fetched)
+template <bool MULTI>
+__device__ __forceinline__ bool better_l(const ScanParams &p, double g, int y, double bg, int by, int &lby) {
+  if (g > bg) { lby = kNoLabel; return true; }
+  if ((g == bg) && (g != 0.0)) {
+    const int ly = label_of<MULTI>(p, y);
+    if (lby == kNoLabel) lby = label_of<MULTI>(p, by);
+    if (ly < lby) { lby = ly; return true; }
+  }
+  return false;
+}
+// dspl.hpp:224: maxIndex > currComm, on labels
+template <bool MULTI>
+__device__ __forceinline__ bool label_greater(const ScanParams &p, int best, int lbest, int cc) {
+  if (best == cc) return false;
+  if (!p.relabel) return best > cc;
+  if (lbest == kNoLabel) lbest = label_of<MULTI>(p, best);
+  return lbest > label_of<MULTI>(p, cc);
 }
 
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
@@ -278,6 +311,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
         ax = __dsub_rn(cc_deg, vdeg);
         double best_gain = 0.0;
         long long best_size = cc_size;
+        int lbest = kNoLabel;
         for (int m = 0; m < nd; m++) {
           const int y = s_comm[o0 + m];
           int yo; long long yi;
@@ -294,9 +328,9 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
             eiy = s_w[o0 + m];
           }
           const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
-          if (better(g, y, best_gain, best)) { best_gain = g; best = y; best_size = ysize; }
+          if (better_l<MULTI>(p, g, y, best_gain, best, lbest)) { best_gain = g; best = y; best_size = ysize; }
         }
-        if (best_size == 1 && cc_size == 1 && best > cc) best = cc;          // dspl.hpp:224-225
+        if (best_size == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lbest, cc)) best = cc;   // dspl.hpp:224-225
         if (best != cc) {                                                    // dspl.hpp:331-399
           int bo; long long bi;
           locate<MULTI>(p.pt, p.base, best, bo, bi);
@@ -312,7 +346,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
         }
       }
       p.tgt[v] = best;                                                       // dspl.hpp:404
-      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(p.base + v, best); }
+      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
     }
     start = end;
     __syncthreads();
@@ -395,16 +429,16 @@ __device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_
   const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
   acc_le += (unsigned long long)cnt0;
   double bg = 0.0;
-  int best = cc;
+  int best = cc, lbest = kNoLabel;
   for (int m = 0; m < nd; m++) {
     const int y = s_comm[o0 + m];
     int yo; long long yi;
     locate<MULTI>(p.pt, p.base, y, yo, yi);
     const double ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
     const double g = gain_of((double)s_cnt[o0 + m], eix, vdeg, ay, ax, p.constant);
-    if (better(g, y, bg, best)) { bg = g; best = y; }
+    if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
   }
-  if (best > cc) {                                                           // dspl.hpp:224-225
+  if (label_greater<MULTI>(p, best, lbest, cc)) {                            // dspl.hpp:224-225
     int bo; long long bi;
     locate<MULTI>(p.pt, p.base, best, bo, bi);
     if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 && __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
@@ -522,14 +556,15 @@ __global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
         const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
         acc_le += (unsigned long long)cnt0;
         double bg = 0.0;
+        int lbest = kNoLabel;
 #pragma unroll
         for (int k = 0; k < kFastDeg; k++) {
           if (rl[k]) {
             const double g = gain_of((double)rl[k], eix, vdeg, (double)dg[k], ax, p.constant);
-            if (better(g, a[k], bg, best)) { bg = g; best = a[k]; }
+            if (better_l<MULTI>(p, g, a[k], bg, best, lbest)) { bg = g; best = a[k]; }
           }
         }
-        if (best > cc) {                                                     // singleton veto, dspl.hpp:224-225
+        if (label_greater<MULTI>(p, best, lbest, cc)) {                      // singleton veto, dspl.hpp:224-225
           int bo; long long bi;
           locate<MULTI>(p.pt, p.base, best, bo, bi);
           if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 &&
@@ -540,7 +575,7 @@ __global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
       }
       if (d <= kFastDeg) {
         st_pol(p.tgt + v, best, pol_str);                                    // dspl.hpp:404
-        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(p.base + v, best); }
+        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
       }
     }
     __syncthreads();
@@ -555,7 +590,7 @@ __global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
       const int sbest = slow_vertex_unit<MULTI>(p, s_comm, s_cnt, (int)(sr0 - E0), sd, sv, scc, acc_le);
       if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
       p.tgt[sv] = sbest;
-      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(p.base + sv, sbest); }
+      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
     }
     start = end;
     __syncthreads();
@@ -616,6 +651,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
   __shared__ double s_g[8];
   __shared__ int s_y[8];
   __shared__ long long s_sz[8];
+  __shared__ int s_l[8];
   if (tid == 0) s_w0 = 0.0;
   __syncthreads();
   for (unsigned int i = tid; i < T; i += blockDim.x)
@@ -638,6 +674,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
   const double w0 = s_w0;
   const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
   double bg = 0.0; int by = cc; long long bsz = cc_size;
+  int lby = kNoLabel;
   for (unsigned int i = tid; i < T; i += blockDim.x) {
     const int y = keys[i];
     if (y < 0 || y == cc) continue;
@@ -652,25 +689,29 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
       ysz = cw.size; ay = cw.degree; eiy = vd[i];
     }
     const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
-    if (better(g, y, bg, by)) { bg = g; by = y; bsz = ysz; }
+    if (better_l<MULTI>(p, g, y, bg, by, lby)) { bg = g; by = y; bsz = ysz; }
   }
-  // CTA argmax under the same ordering.  `better` needs care when combining partial winners that
+  if (by != cc && lby == kNoLabel) lby = label_of<MULTI>(p, by);   // partial winners carry their label into the reduction
+  // CTA argmax under the same ordering (labels compared where the reference compares ids).  `better` needs care when combining partial winners that
   // still sit at the initial state (gain 0, id cc): an initial state never beats a real candidate.
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     const double og = __shfl_xor_sync(0xffffffffu, bg, o);
     const int oy = __shfl_xor_sync(0xffffffffu, by, o);
     const long long os = __shfl_xor_sync(0xffffffffu, bsz, o);
-    if (oy != cc && (by == cc || better(og, oy, bg, by))) { bg = og; by = oy; bsz = os; }
+    const int ol = __shfl_xor_sync(0xffffffffu, lby, o);
+    if (oy != cc && (by == cc || (og > bg) || ((og == bg) && (og != 0.0) && (ol < lby)))) { bg = og; by = oy; bsz = os; lby = ol; }
   }
-  if ((tid & 31) == 0) { s_g[tid >> 5] = bg; s_y[tid >> 5] = by; s_sz[tid >> 5] = bsz; }
+  if ((tid & 31) == 0) { s_g[tid >> 5] = bg; s_y[tid >> 5] = by; s_sz[tid >> 5] = bsz; s_l[tid >> 5] = lby; }
   __syncthreads();
   if (tid == 0) {
-    bg = 0.0; by = cc; bsz = cc_size;
+    bg = 0.0; by = cc; bsz = cc_size; lby = kNoLabel;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++)
-      if (s_y[w] != cc && (by == cc || better(s_g[w], s_y[w], bg, by))) { bg = s_g[w]; by = s_y[w]; bsz = s_sz[w]; }
+      if (s_y[w] != cc && (by == cc || (s_g[w] > bg) || ((s_g[w] == bg) && (bg != 0.0) && (s_l[w] < lby)))) {
+        bg = s_g[w]; by = s_y[w]; bsz = s_sz[w]; lby = s_l[w];
+      }
     int best = by;
-    if (bsz == 1 && cc_size == 1 && best > cc) best = cc;
+    if (bsz == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lby, cc)) best = cc;
     if (best != cc) {
       int bo; long long bi;
       locate<MULTI>(p.pt, p.base, best, bo, bi);
@@ -686,7 +727,10 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     }
     p.tgt[v] = best;
     if (UNIT) atomicAdd(&p.acc->le_u, (unsigned long long)w0); else atomicAdd(&p.acc->le_d, w0);
-    if (TRACE) { atomicAdd(&p.acc->moved, (unsigned long long)(best != cc)); atomicAdd(&p.acc->hash, vhash(p.base + v, best)); }
+    if (TRACE) {
+      atomicAdd(&p.acc->moved, (unsigned long long)(best != cc));
+      atomicAdd(&p.acc->hash, vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)));
+    }
   }
 }
 
@@ -869,12 +913,125 @@ __global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *
     if (rowptr[v + 1] - rowptr[v] > heavy_deg) list[atomicAdd(count, 1u)] = v;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Locality renumbering (B200 layout step, not in the reference).  miniVite numbers RGG vertices in
+// generation order, i.e. randomly in space, so cur[tail] gathers have no locality and every edge costs a
+// DRAM sector.  We grow ~lnv/4096 regions simultaneously by breadth-first search from evenly spaced seed
+// ids (one persistent cooperative kernel, one grid barrier per level) and renumber vertices by
+// (region, BFS level): neighbours end up a few KB apart, so gathers hit L1/L2.  Results are unchanged:
+// the algorithm is a synchronous (Jacobi) sweep, and wherever the reference compares community ids the
+// kernels compare the original ids kept as labels.
+// key = level << 22 | region  (atomicMin: lowest level wins, then lowest region -> deterministic)
+// ----------------------------------------------------------------------------------------------
+constexpr unsigned int kBfsRegionBits = 22;
+constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
+                                               int region_stride, int max_levels, unsigned int *level_flags) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (int v = gtid; v < lnv; v += gsz)
+    key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
+  grid.sync();
+  for (int level = 0; level < max_levels; level++) {
+    bool any = false;
+    for (int v = gtid; v < lnv; v += gsz) {
+      const unsigned int k = __ldcg(key + v);
+      if ((k >> kBfsRegionBits) == (unsigned int)level && k != kBfsUnreached) {
+        any = true;
+        const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (k & ((1u << kBfsRegionBits) - 1));
+        const uint32_t e1 = rowptr[v + 1];
+        for (uint32_t e = rowptr[v]; e < e1; e++) {
+          const int w = tails[e];
+          if (w < lnv && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
+        }
+      }
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) level_flags[level] = 1;
+    grid.sync();
+    if (__ldcg(level_flags + level) == 0) break;
+  }
+}
+
+// sort key: region major, level minor; unreached vertices (other components) last, in id order
+__global__ void __launch_bounds__(256) k_bfs_sortkeys(int lnv, const uint32_t *key, uint32_t *sortkey, int32_t *ids) {
+  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
+    const unsigned int k = key[v];
+    unsigned int sk;
+    if (k == kBfsUnreached) sk = 0xFFFFFFFFu;
+    else {
+      const unsigned int region = k & ((1u << kBfsRegionBits) - 1), level = min(k >> kBfsRegionBits, 1023u);
+      sk = (region << 10) | level;
+    }
+    sortkey[v] = sk;
+    ids[v] = v;
+  }
+}
+
+// perm[new] = old  ->  inv[old] = new, lab[new] = global original id
+__global__ void __launch_bounds__(256) k_perm_inverse(int lnv, const int32_t *perm, long long base, int32_t *inv, int32_t *lab,
+                                                      const uint32_t *rowptr_old, uint32_t *deg_new) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= lnv; i += gridDim.x * blockDim.x) {
+    if (i == lnv) { deg_new[i] = 0; continue; }
+    const int o = perm[i];
+    inv[o] = i;
+    lab[i] = (int32_t)(base + o);
+    deg_new[i] = rowptr_old[o + 1] - rowptr_old[o];
+  }
+}
+
+// adjacency of new vertex i := adjacency of old vertex perm[i], tails renumbered (ghost slots unchanged),
+// edge order preserved (weighted sums keep the reference's summation order)
+__global__ void __launch_bounds__(256) k_permute_adj(int lnv, const int32_t *perm, const int32_t *inv, const uint32_t *rowptr_old,
+                                                     const int32_t *tails_old, const double *w_old, const uint32_t *rowptr_new,
+                                                     int32_t *tails_new, double *w_new) {
+  const int lane = threadIdx.x & 7;
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ntiles = (gridDim.x * blockDim.x) >> 3;
+  for (int i = tile; i < lnv; i += ntiles) {
+    const int o = perm[i];
+    const uint32_t s0 = rowptr_old[o], s1 = rowptr_old[o + 1], d0 = rowptr_new[i];
+    for (uint32_t k = lane; k < s1 - s0; k += 8) {
+      const int t = tails_old[s0 + k];
+      tails_new[d0 + k] = (t < lnv) ? inv[t] : t;
+      if (w_old) w_new[d0 + k] = w_old[s0 + k];
+    }
+  }
+}
+
+// average |tail - v| over a sample of edges: decides whether the given numbering already has locality
+__global__ void __launch_bounds__(256) k_span_sample(int lnv, const uint32_t *rowptr, const int32_t *tails, int stride,
+                                                     unsigned long long *span_sum, unsigned long long *span_cnt) {
+  unsigned long long s = 0, c = 0;
+  for (int v = (blockIdx.x * blockDim.x + threadIdx.x) * stride; v < lnv; v += gridDim.x * blockDim.x * stride) {
+    const uint32_t e1 = rowptr[v + 1];
+    for (uint32_t e = rowptr[v]; e < e1; e++) {
+      const int t = tails[e];
+      if (t < lnv) { s += (unsigned long long)abs(t - v); c++; }
+    }
+  }
+  s = warp_sum(s); c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c) { atomicAdd(span_sum, s); atomicAdd(span_cnt, c); }
+}
+
+// final assignment in the caller's numbering: out[old local vertex] = label of its community
+template <bool MULTI>
+__global__ void __launch_bounds__(256) k_final_labels(int lnv, const int32_t *cur, const int32_t *perm, ScanParams p, int32_t *out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lnv; i += gridDim.x * blockDim.x) {
+    const int c = cur[i];
+    out[perm ? perm[i] : i] = label_of<MULTI>(p, c);
+  }
+}
+
 // ghost exchange helpers (dspl.hpp:559-571): pack the communities peers asked for; global -> local ids
 __global__ void __launch_bounds__(256) k_pack_send(const int32_t *comm, const int32_t *send_lid, int n, int32_t *out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = comm[send_lid[i]];
 }
 __global__ void __launch_bounds__(256) k_gid_to_lid(const long long *gid, int n, long long base, int32_t *lid) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) lid[i] = (int32_t)(gid[i] - base);
+}
+__global__ void __launch_bounds__(256) k_apply_inv(int32_t *lid, int n, const int32_t *inv) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) lid[i] = inv[lid[i]];
 }
 __global__ void __launch_bounds__(256) k_init_ghost_comm(const long long *ghost_gid, int n, int32_t *comm_ghost) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) comm_ghost[i] = (int32_t)ghost_gid[i];

@@ -66,8 +66,8 @@ struct DevBuf {              // grow-only device buffer (allocations are cached 
 };
 
 struct PeerBlob {            // what every rank publishes about its community arrays
-  cudaIpcMemHandle_t h[6];
-  unsigned long long raw[6];
+  cudaIpcMemHandle_t h[7];
+  unsigned long long raw[7];
   int pid, device, unit, pad;
 };
 
@@ -94,6 +94,14 @@ struct mvgpu_ctx {
   DevBuf<int32_t> tails;
   DevBuf<double> weights;
   DevBuf<int32_t> self_i;
+  // locality renumbering
+  DevBuf<uint32_t> bfs_key, sortkey, sortkey2, deg_new, rowptr2;
+  DevBuf<int32_t> ids, perm, inv, lab, tails2, final_orig;
+  DevBuf<double> weights2;
+  DevBuf<unsigned int> level_flags;
+  bool reordered = false;
+  int relabel = 0;
+  double reorder_s = 0.0;
   DevBuf<double> self_d, vdeg;
   // state
   DevBuf<int32_t> comm_a, comm_b;
@@ -123,7 +131,7 @@ struct mvgpu_ctx {
   bool peers_ready = false;
   int peers_unit = -1;
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 1, opt_cache_policy = 5;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 1, opt_cache_policy = 5, opt_reorder = 2, opt_region = 4096;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -137,6 +145,7 @@ struct mvgpu_ctx {
   void *h_pin = nullptr;
   // events
   std::vector<cudaEvent_t> events;
+  ScanParams last_sp;
 };
 
 namespace {
@@ -169,6 +178,7 @@ struct Scalars {
   double red2[2];
   unsigned long long tr2[2];
   long long counts[2 * kMaxRanks];
+  unsigned long long span_sum, span_cnt;
 };
 
 int set_graph(mvgpu_ctx *c, long long nv_global, const int64_t *parts, long long lnv, long long lne) {
@@ -194,18 +204,19 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   pt.nranks = c->nranks; pt.rank = c->rank;
   for (int r = 0; r <= c->nranks; r++) pt.parts[r] = c->parts[r];
   if (c->nranks == 1) {
+    pt.lab[0] = c->relabel ? c->lab.p : nullptr;
     pt.cdeg[0] = c->cdeg.p; pt.csize[0] = c->csize.p; pt.upd[0] = c->upd.p; pt.cinfo_w[0] = c->cinfo_w.p; pt.usize[0] = c->usize.p; pt.udeg[0] = c->udeg.p;
     return 0;
   }
-  if (c->peers_ready && c->peers_unit == unit) return 0;
+  if (c->peers_ready && c->peers_unit == unit * 2 + c->relabel) return 0;
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
   PeerBlob mine;
   memset(&mine, 0, sizeof mine);
-  void *ptrs[6] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
+  void *ptrs[7] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
                    unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
-                   unit ? nullptr : (void *)c->udeg.p};
-  for (int k = 0; k < 6; k++) {
+                   unit ? nullptr : (void *)c->udeg.p, c->relabel ? (void *)c->lab.p : nullptr};
+  for (int k = 0; k < 7; k++) {
     mine.raw[k] = (unsigned long long)ptrs[k];
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
   }
@@ -219,9 +230,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   CK(cudaStreamSynchronize(c->stream));
   d_all.release();
   for (int r = 0; r < c->nranks; r++) {
-    void *q[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *q[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (all[r].unit != unit) return fail("ranks disagree on the unit-weight path");
-    if (r == c->rank) { for (int k = 0; k < 6; k++) q[k] = ptrs[k]; }
+    if (r == c->rank) { for (int k = 0; k < 7; k++) q[k] = ptrs[k]; }
     else if (all[r].pid == mine.pid) {           // same process (threads): plain UVA pointers + peer access
       int can = 0;
       CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
@@ -229,9 +240,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
       cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
       cudaGetLastError();
-      for (int k = 0; k < 6; k++) q[k] = (void *)all[r].raw[k];
+      for (int k = 0; k < 7; k++) q[k] = (void *)all[r].raw[k];
     } else {
-      for (int k = 0; k < 6; k++)
+      for (int k = 0; k < 7; k++)
         if (all[r].raw[k]) {
           CK(cudaIpcOpenMemHandle(&q[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess));
           c->ipc_opened.push_back(q[k]);
@@ -239,9 +250,10 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     }
     pt.cdeg[r] = (const uint32_t *)q[0]; pt.csize[r] = (const int32_t *)q[1]; pt.upd[r] = (unsigned long long *)q[2];
     pt.cinfo_w[r] = (const CommW *)q[3]; pt.usize[r] = (long long *)q[4]; pt.udeg[r] = (double *)q[5];
+    pt.lab[r] = (const int32_t *)q[6];
   }
   c->peers_ready = true;
-  c->peers_unit = unit;
+  c->peers_unit = unit * 2 + c->relabel;
   return 0;
 }
 
@@ -276,6 +288,8 @@ int launch_scan(mvgpu_ctx *c, const ScanParams &sp) {
 #undef MV_CASE
   return fail("unreachable");
 }
+
+int exchange_ghosts(mvgpu_ctx *c, int32_t *comm);
 
 // ---- setup: reference-format arrays -> compact graph, ghosts, init ------------------------------
 int setup_run(mvgpu_ctx *c) {
@@ -395,6 +409,86 @@ int setup_run(mvgpu_ctx *c) {
     }
   }
 
+  // ---- locality renumbering (see kernels.cuh): decide, then BFS regions -> sort -> permute the compact CSR
+  c->reordered = false;
+  c->relabel = 0;
+  {
+    int want = c->opt_reorder == 1 ? 1 : 0;
+    if (c->opt_reorder == 2 && lnv >= 65536) {
+      // auto: renumber when the given numbering has no locality (mean |tail - v| above lnv/64 on a vertex sample)
+      k_span_sample<<<grid_for(lnv / 64 + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->rowptr.p, c->tails.p, 64, &d_sc->span_sum, &d_sc->span_cnt);
+      c->tm.kernel_launches++;
+      unsigned long long sp2[2];
+      CK(cudaMemcpyAsync(sp2, &d_sc->span_sum, sizeof sp2, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (sp2[1] > 0 && (double)sp2[0] / (double)sp2[1] > (double)lnv / 64.0) want = 1;
+    }
+    int any = want;
+    if (c->nranks > 1) {
+      long long hv = want;
+      CK(cudaMemcpyAsync(d_sc->counts, &hv, sizeof hv, cudaMemcpyHostToDevice, s));
+      NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclMax, c->comm, s));
+      CK(cudaMemcpyAsync(&hv, d_sc->counts, sizeof hv, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      any = hv != 0;
+    }
+    c->relabel = any;                       // labels are needed everywhere as soon as one rank renumbers
+    if (any && lnv > 0) {
+      cudaEvent_t r0 = get_event(c, 2), r1 = get_event(c, 3);
+      CK(cudaEventRecord(r0, s));
+      TRY(c->perm.ensure(lnv)); TRY(c->inv.ensure(lnv)); TRY(c->lab.ensure(lnv)); TRY(c->ids.ensure(lnv));
+      TRY(c->bfs_key.ensure(lnv)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
+      TRY(c->deg_new.ensure(lnv + 1)); TRY(c->rowptr2.ensure(lnv + 1)); TRY(c->tails2.ensure(lne));
+      if (!c->unit) TRY(c->weights2.ensure(lne));
+      const int max_levels = 1023;
+      TRY(c->level_flags.ensure(max_levels + 1));
+      CK(cudaMemsetAsync(c->level_flags.p, 0, sizeof(unsigned int) * (max_levels + 1), s));
+      if (want) {
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msbfs, 256, 0));
+        if (occ < 1) return fail("k_msbfs cannot be made resident");
+        int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
+        const uint32_t *rp = c->rowptr.p; const int32_t *tl = c->tails.p; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
+        CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
+        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s);
+        TRY(c->cub_tmp.ensure(tb));
+        tb = c->cub_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s));
+        c->tm.kernel_launches += 3;
+      } else {
+        // another rank renumbers, this one keeps its order: identity permutation, labels still required
+        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->perm.p);
+        c->tm.kernel_launches++;
+      }
+      k_perm_inverse<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->perm.p, c->base, c->inv.p, c->lab.p, c->rowptr.p, c->deg_new.p);
+      c->tm.kernel_launches++;
+      if (want) {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, c->deg_new.p, c->rowptr2.p, (int)lnv + 1, s);
+        TRY(c->cub_tmp.ensure(tb));
+        tb = c->cub_tmp.cap;
+        CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, c->deg_new.p, c->rowptr2.p, (int)lnv + 1, s));
+        k_permute_adj<<<grid_for(lnv * 8, 256, nsm, 16), 256, 0, s>>>((int)lnv, c->perm.p, c->inv.p, c->rowptr.p, c->tails.p,
+                                                                    c->unit ? nullptr : c->weights.p, c->rowptr2.p, c->tails2.p,
+                                                                    c->unit ? nullptr : c->weights2.p);
+        c->tm.kernel_launches += 2;
+        std::swap(c->rowptr, c->rowptr2);
+        std::swap(c->tails, c->tails2);
+        if (!c->unit) std::swap(c->weights, c->weights2);
+        c->reordered = true;
+      }
+      CK(cudaEventRecord(r1, s));
+    }
+    // peers asked for my vertices by ORIGINAL id: the send list holds their current (internal) local index
+    if (c->relabel && c->nsend) {
+      k_apply_inv<<<grid_for(c->nsend, 256, nsm), 256, 0, s>>>(c->send_lid.p, (int)c->nsend, c->inv.p);
+      c->tm.kernel_launches++;
+    }
+  }
+
   // state arrays
   const long long nslots = lnv + c->nghost;
   TRY(c->comm_a.ensure(nslots));
@@ -413,10 +507,9 @@ int setup_run(mvgpu_ctx *c) {
                                                                nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
                                                                nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self);
   c->tm.kernel_launches++;
-  if (c->nghost) {
-    k_init_ghost_comm<<<grid_for(c->nghost, 256, nsm), 256, 0, s>>>(c->ghost_gid.p, (int)c->nghost, c->comm_a.p + lnv);
-    c->tm.kernel_launches++;
-  }
+  // ghosts start in their own (internal) singleton community, which only the owner knows after renumbering:
+  // fetch it with the same all-to-all-v the iterations use
+  if (c->nranks > 1) TRY(exchange_ghosts(c, c->comm_a.p));
 
   // high-degree vertices
   const long long heavy_deg = (c->opt_force_heavy_deg > 0) ? std::min<long long>(c->opt_force_heavy_deg, kECap) : kECap;
@@ -490,6 +583,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   c->scan_times.clear();
   size_t ev = 0;
   cudaEvent_t e_begin = get_event(c, ev++), e_setup = get_event(c, ev++);
+  ev = 4;                                   // events 2,3 bracket the renumbering inside setup_run
   CK(cudaEventRecord(e_begin, s));
   TRY(setup_run(c));
   CK(cudaEventRecord(e_setup, s));
@@ -500,10 +594,12 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   memset(&sp, 0, sizeof sp);
   sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.base = c->base;
   sp.cache_policy = c->opt_cache_policy;
+  sp.relabel = c->relabel;
   sp.rowptr = c->rowptr.p; sp.tails = c->tails.p; sp.weights = c->unit ? nullptr : c->weights.p;
   sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
   sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
   sp.pt = c->pt;
+  c->last_sp = sp;
 
   struct HostMail { Acc acc; double red2[2]; unsigned long long tr2[2]; };
   HostMail *mail = reinterpret_cast<HostMail *>(c->h_pin);
@@ -577,6 +673,8 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e_begin, e_end)); c->tm.total_s = ms * 1e-3;
   CK(cudaEventElapsedTime(&ms, e_begin, e_setup)); c->tm.setup_s = ms * 1e-3;
+  if (c->relabel && c->lnv > 0) { CK(cudaEventElapsedTime(&ms, c->events[2], c->events[3])); c->tm.reorder_s = ms * 1e-3; }
+  c->tm.reordered = c->reordered ? 1 : 0;
   for (int k = 0; k < numIters; k++) {
     cudaEvent_t e0 = c->events[ev_iter0 + 4 * k], e1 = c->events[ev_iter0 + 4 * k + 1], e2 = c->events[ev_iter0 + 4 * k + 2],
                 e3 = c->events[ev_iter0 + 4 * k + 3];
@@ -644,6 +742,9 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
   c->scratch.release(); c->cub_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
+  c->bfs_key.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
+  c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
+  c->weights2.release(); c->level_flags.release();
   c->send_lid.release(); c->send_buf.release(); c->heavy_list.release(); c->hkeys.release(); c->hvals_i.release();
   c->hvals_d.release(); c->heavy_off.release();
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -710,19 +811,33 @@ int mvgpu_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters, double 
   return run_louvain(c, lower, thresh, iters, modularity);
 }
 
+// currComm in the caller's vertex numbering, as labels (original global ids)
+static int final_in_caller_order(mvgpu_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  TRY(c->final_orig.ensure(c->lnv));
+  if (c->lnv == 0) return 0;
+  const int32_t *perm = c->reordered ? c->perm.p : nullptr;
+  if (c->nranks > 1) k_final_labels<true><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
+  else k_final_labels<false><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 int mvgpu_get_communities_device(mvgpu_ctx *c, const int32_t **d_out) {
   if (!c || !c->d_final) return fail("no result yet");
-  *d_out = c->d_final;
+  TRY(final_in_caller_order(c));
+  CK(cudaStreamSynchronize(c->stream));
+  *d_out = c->final_orig.p;
   return 0;
 }
 
 int mvgpu_get_communities(mvgpu_ctx *c, int64_t *out) {
   if (!c || !c->d_final) return fail("no result yet");
-  CK(cudaSetDevice(c->device));
   if (c->lnv == 0) return 0;
+  TRY(final_in_caller_order(c));
   DevBuf<long long> wide;
   TRY(wide.ensure(c->lnv));
-  k_widen<<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>(c->d_final, c->lnv, wide.p);
+  k_widen<<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>(c->final_orig.p, c->lnv, wide.p);
   CK(cudaMemcpyAsync(out, wide.p, sizeof(long long) * c->lnv, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   wide.release();
@@ -738,6 +853,8 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
   else if (n == "scan_variant") c->opt_scan_variant = (int)value;
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
+  else if (n == "reorder") c->opt_reorder = (int)value;
+  else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;
 }

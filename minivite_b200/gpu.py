@@ -19,7 +19,8 @@ class Timings(ctypes.Structure):
     _fields_ = [("total_s", ctypes.c_double), ("setup_s", ctypes.c_double), ("scan_s", ctypes.c_double),
                 ("fold_s", ctypes.c_double), ("exchange_s", ctypes.c_double), ("h2d_s", ctypes.c_double),
                 ("scan_launches", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
-                ("iters", ctypes.c_int32), ("unit_weight", ctypes.c_int32)]
+                ("iters", ctypes.c_int32), ("unit_weight", ctypes.c_int32), ("reorder_s", ctypes.c_double),
+                ("reordered", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

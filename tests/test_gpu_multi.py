@@ -98,6 +98,17 @@ def test_multi_gpu_partition_invariance(tmp_path, golden):
     check(res, golden["rgg_n16384_p1"])
 
 
+def test_multi_gpu_with_renumbering(tmp_path, golden):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    for name in ("rgg_n16384_p2", "hand_clique_ring_p2", "file_rgg_n16384_s1_p2"):
+        res = run_ranks(tmp_path, 2, name, reorder=1, region_size=64)
+        assert res["timings"]["reordered"] == 1
+        check(res, golden[name])
+    res = run_ranks(tmp_path, 2, "rgg_n16384_p2", reorder=1, region_size=64, scan_variant=0)
+    check(res, golden["rgg_n16384_p2"])
+
+
 def test_multi_gpu_weighted_and_heavy(tmp_path, golden):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")

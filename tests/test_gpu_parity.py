@@ -197,3 +197,27 @@ def test_full_size_config2_matches_reference_trace(gpu):
     # size-independent properties: community ids are vertex ids of members' lineage, sizes add up
     comm = res["comm"]
     assert comm.min() >= 0 and comm.max() < gold["nv"]
+
+
+def test_locality_renumbering_keeps_results(gpu, golden):
+    """reorder=1 renumbers vertices by BFS regions (layout only): traces, final assignment (in the caller's
+    numbering, as original ids) and modularity must stay bit-identical to the reference, for every kernel variant."""
+    names = ["rgg_n16384_p1", "rgg_n65536_p1", "hand_path16_p1", "hand_two_triangles_p1", "hand_k66_p1",
+             "hand_loops_multi_p1", "hand_clique_ring_p1", "hand_star41_p1", "file_rgg_n32768_s8_p1", "rgg_n16384_p2_l"]
+    for name in names:
+        case = golden[name]
+        nv, parts, rowptr, edges = as_single(case)
+        for opts in ({"reorder": 1, "region_size": 64}, {"reorder": 1, "region_size": 4096, "scan_variant": 0},
+                     {"reorder": 1, "region_size": 32, "force_heavy_deg": 3}):
+            res = run_single(gpu, parts, rowptr, edges, nv, **opts)
+            assert res["timings"]["reordered"] == 1, (name, opts)
+            assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
+    case = golden["rgg_n16384_p1"]
+    nv, parts, rowptr, edges = as_single(case)
+    res = run_single(gpu, parts, rowptr, edges, nv, reorder=1, force_weighted=1)
+    assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"] if "comm" in case else None)
+    # weighted graph: renumbering keeps the per-vertex edge order, so sums round the same way
+    case = golden["rgg_n16384_p1_w"]
+    nv, parts, rowptr, edges = as_single(case)
+    res = run_single(gpu, parts, rowptr, edges, nv, reorder=1, region_size=128)
+    assert abs(res["modularity"] - float(case["modularity"])) <= 1e-6

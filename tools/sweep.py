@@ -31,6 +31,6 @@ for spec in sys.argv[2:]:
     tm = ctx.timings()
     st = ctx.scan_times() * 1e3
     print(f"{spec:40s} mod={mod:.17g} iters={iters} total={tm['total_s']*1e3:8.3f}ms scan={tm['scan_s']*1e3:8.3f}ms "
-          f"avg={tm['scan_s']/iters*1e3:.3f} first3={st[0]:.2f},{st[1]:.2f},{st[2]:.2f} last={st[-1]:.2f} fold={tm['fold_s']*1e3:.2f} setup={tm['setup_s']*1e3:.2f}",
+          f"avg={tm['scan_s']/iters*1e3:.3f} first3={st[0]:.2f},{st[1]:.2f},{st[2]:.2f} last={st[-1]:.2f} fold={tm['fold_s']*1e3:.2f} setup={tm['setup_s']*1e3:.2f} reorder={tm['reorder_s']*1e3:.2f}",
           flush=True)
     ctx.close()
