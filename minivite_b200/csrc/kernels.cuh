@@ -617,6 +617,266 @@ __global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Scan kernel, third generation ("register cache"): same tiles and phase A as k_scan; in phase B each thread
+// walks its vertex's staged neighbours ONCE, in edge order, keeping up to kRcK distinct neighbour communities and
+// their weight sums in registers (straight-line compare/accumulate code, no inner search loop, no shared-memory
+// writes).  After the first few iterations almost every vertex sees only a handful of communities, so the
+// divergent O(d * distinct) in-place reduction of k_scan is replaced by O(d) uniform work; vertices that overflow
+// the cache (common only in iterations 1-3) are queued and reduced afterwards by the generic in-place code,
+// packed densely into the first warps.  Sums are accumulated sequentially in edge order, so this kernel also
+// serves the weighted (fp64) path with the reference's summation order.
+// ----------------------------------------------------------------------------------------------
+constexpr int kRcK = 6;
+
+// generic in-place reduction of one vertex's staged segment (any degree <= kECap), weighted
+template <bool MULTI>
+__device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_comm, double *s_w, int o0, int d, int v, int cc,
+                                             double &acc_le, double &vdeg_out) {
+  int nd = 0;
+  double w0 = 0.0;
+  for (int k = 0; k < d; k++) {
+    const int ck = s_comm[o0 + k];
+    if (ck == cc) { w0 += s_w[o0 + k]; continue; }
+    if (ck < 0) continue;
+    double sum = s_w[o0 + k];
+    for (int j = k + 1; j < d; j++)
+      if (s_comm[o0 + j] == ck) { sum += s_w[o0 + j]; s_comm[o0 + j] = -1; }
+    s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
+  }
+  int owner; long long idx;
+  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  const double2 raw = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx));
+  const long long cc_size = __double_as_longlong(raw.x);
+  const double vdeg = __ldg(p.vdeg + v);
+  vdeg_out = vdeg;
+  const double sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
+  const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(raw.y, vdeg);
+  acc_le += w0;
+  double bg = 0.0;
+  int best = cc, lbest = kNoLabel;
+  long long best_size = cc_size;
+  for (int m = 0; m < nd; m++) {
+    const int y = s_comm[o0 + m];
+    int yo; long long yi;
+    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    const double2 ry = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi));
+    const double g = gain_of(s_w[o0 + m], eix, vdeg, ry.y, ax, p.constant);
+    if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; best_size = __double_as_longlong(ry.x); }
+  }
+  if (best_size == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lbest, cc)) best = cc;
+  return best;
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int best, double vdeg) {
+  int bo, co; long long bi, ci;
+  locate<MULTI>(p.pt, p.base, best, bo, bi);
+  locate<MULTI>(p.pt, p.base, cc, co, ci);
+  atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
+  atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
+  atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[co] : p.pt.usize[0]) + ci), ~0ULL);
+  atomicAdd((MULTI ? p.pt.udeg[co] : p.pt.udeg[0]) + ci, -vdeg);
+}
+
+template <bool UNIT, bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(kTileV, 4) k_scan_rc(const ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);
+  int32_t *s_cnt = s_comm + kECap;
+  double *s_w = reinterpret_cast<double *>(smem_raw + sizeof(int32_t) * kECap);
+  __shared__ int s_next, s_nslow, s_end, s_skip;
+  __shared__ uint32_t s_e0;
+  __shared__ int s_slow[kTileV];
+  __shared__ unsigned long long s_red[3][kTileV / 32];
+  __shared__ double s_redd[kTileV / 32];
+
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileV;
+  const int v1 = min(p.lnv, v0 + kTileV);
+  const int v = v0 + tid;
+  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
+  uint32_t r0 = 0, r1 = 0;
+  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
+  const uint32_t deg = r1 - r0;
+  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
+  unsigned long long acc_le_u = 0, acc_moved = 0, acc_hash = 0;
+  double acc_le_d = 0.0;
+
+  int start = v0;
+  while (start < v1) {
+    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
+    __syncthreads();
+    if (s_skip) { start++; __syncthreads(); continue; }
+    const uint32_t E0 = s_e0;
+    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
+    __syncthreads();
+    const int end = s_end;
+    if (tid == end - 1 - v0) s_next = (int)r1;
+    __syncthreads();
+    const int ne = (int)((uint32_t)s_next - E0);
+
+    // ---- phase A
+    {
+      const int32_t *tl = p.tails + E0;
+      int i = tid;
+      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
+        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
+                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
+        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
+        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      }
+      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
+      if (!UNIT) {
+        const double *wl = p.weights + E0;
+        for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B, pass 1: register cache of distinct neighbour communities
+    if (v >= start && v < end) {
+      const int cc = __ldg(p.cur + v);
+      int best = cc;
+      bool done = true;
+      const int d = (int)deg;
+      if (d != 0) {
+        const int o0 = (int)(r0 - E0);
+        int ck[kRcK];
+        double nk[kRcK];                       // unit: exact small integers
+#pragma unroll
+        for (int i = 0; i < kRcK; i++) { ck[i] = -1; nk[i] = 0.0; }
+        int nd = 0;
+        double w0 = 0.0;
+        bool overflow = false;
+        for (int k = 0; k < d; k++) {
+          const int c = s_comm[o0 + k];
+          const double w = UNIT ? 1.0 : s_w[o0 + k];
+          if (c == cc) { w0 += w; continue; }
+          bool hit = false;
+#pragma unroll
+          for (int i = 0; i < kRcK; i++)
+            if (ck[i] == c) { nk[i] += w; hit = true; }
+          if (!hit) {
+            if (nd == kRcK) { overflow = true; break; }
+#pragma unroll
+            for (int i = 0; i < kRcK; i++)
+              if (i == nd) { ck[i] = c; nk[i] = w; }
+            nd++;
+          }
+        }
+        if (overflow) { done = false; s_slow[atomicAdd(&s_nslow, 1)] = tid; }
+        else {
+          int owner; long long idx;
+          locate<MULTI>(p.pt, p.base, cc, owner, idx);
+          double cc_deg, vdeg, sl;
+          if (UNIT) {
+            cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+            vdeg = (double)d;
+            sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
+            acc_le_u += (unsigned long long)w0;
+          } else {
+            cc_deg = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->degree);
+            vdeg = __ldg(p.vdeg + v);
+            sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
+            acc_le_d += w0;
+          }
+          const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
+          double ay[kRcK];
+#pragma unroll
+          for (int i = 0; i < kRcK; i++) {
+            ay[i] = 0.0;
+            if (i < nd) {
+              int yo; long long yi;
+              locate<MULTI>(p.pt, p.base, ck[i], yo, yi);
+              if (UNIT) ay[i] = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+              else ay[i] = __ldg(&((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi)->degree);
+            }
+          }
+          double bg = 0.0;
+          int lbest = kNoLabel;
+#pragma unroll
+          for (int i = 0; i < kRcK; i++) {
+            if (i < nd) {
+              const double g = gain_of(nk[i], eix, vdeg, ay[i], ax, p.constant);
+              if (better_l<MULTI>(p, g, ck[i], bg, best, lbest)) { bg = g; best = ck[i]; }
+            }
+          }
+          if (label_greater<MULTI>(p, best, lbest, cc)) {                    // singleton veto, dspl.hpp:224-225
+            int bo; long long bi;
+            locate<MULTI>(p.pt, p.base, best, bo, bi);
+            long long sz_cc, sz_b;
+            if (UNIT) {
+              sz_cc = __ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
+              sz_b = __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi);
+            } else {
+              sz_cc = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->size);
+              sz_b = __ldg(&((MULTI ? p.pt.cinfo_w[bo] : p.pt.cinfo_w[0]) + bi)->size);
+            }
+            if (sz_cc == 1 && sz_b == 1) best = cc;
+          }
+          if (best != cc) {                                                  // dspl.hpp:331-399
+            if (UNIT) push_move_unit<MULTI>(p, cc, best, d);
+            else push_move_w<MULTI>(p, cc, best, vdeg);
+          }
+        }
+      }
+      if (done) {
+        st_pol(p.tgt + v, best, pol_str);                                    // dspl.hpp:404
+        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
+      }
+    }
+    __syncthreads();
+    // ---- phase B, pass 2: cache overflows, generic in-place reduction, packed into the first warps
+    const int nslow = s_nslow;
+    for (int q = tid; q < nslow; q += kTileV) {
+      const int sv = v0 + s_slow[q];
+      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
+      const int scc = __ldg(p.cur + sv);
+      const int sd = (int)(sr1 - sr0);
+      int sbest;
+      if (UNIT) {
+        sbest = slow_vertex_unit<MULTI>(p, s_comm, s_cnt, (int)(sr0 - E0), sd, sv, scc, acc_le_u);
+        if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
+      } else {
+        double svdeg;
+        sbest = slow_vertex_w<MULTI>(p, s_comm, s_w, (int)(sr0 - E0), sd, sv, scc, acc_le_d, svdeg);
+        if (sbest != scc) push_move_w<MULTI>(p, scc, sbest, svdeg);
+      }
+      p.tgt[sv] = sbest;
+      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
+    }
+    start = end;
+    __syncthreads();
+  }
+
+  const int lane = tid & 31, wid = tid >> 5;
+  if (UNIT) { const unsigned long long s = warp_sum(acc_le_u); if (lane == 0) s_red[0][wid] = s; }
+  else { const double s = warp_sum(acc_le_d); if (lane == 0) s_redd[wid] = s; }
+  if (TRACE) {
+    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
+    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (UNIT) {
+      unsigned long long s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
+      if (s) atomicAdd(&p.acc->le_u, s);
+    } else {
+      double s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
+      if (s != 0.0) atomicAdd(&p.acc->le_d, s);
+    }
+    if (TRACE) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
+      atomicAdd(&p.acc->moved, a);
+      atomicAdd(&p.acc->hash, b);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // High-degree vertices (degree > heavy_deg): one CTA per vertex, open-addressing table in HBM
 // scratch (2x degree entries) keyed by neighbour community; same decision rule.  Weighted sums are
 // accumulated with fp64 atomics here (order not fixed: weighted parity is tolerance-based anyway).
@@ -934,15 +1194,27 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
   for (int v = gtid; v < lnv; v += gsz)
     key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
   grid.sync();
+  const int lane = threadIdx.x & 31;
   for (int level = 0; level < max_levels; level++) {
     bool any = false;
-    for (int v = gtid; v < lnv; v += gsz) {
-      const unsigned int k = __ldcg(key + v);
-      if ((k >> kBfsRegionBits) == (unsigned int)level && k != kBfsUnreached) {
-        any = true;
-        const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (k & ((1u << kBfsRegionBits) - 1));
-        const uint32_t e1 = rowptr[v + 1];
-        for (uint32_t e = rowptr[v]; e < e1; e++) {
+    // every warp inspects 32 consecutive keys; the (few) frontier vertices among them are expanded by the
+    // whole warp, lanes over edges, so the random key[] probes of one vertex are in flight together
+    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
+      const int v = vb + lane;
+      unsigned int k = kBfsUnreached;
+      if (v < lnv) k = __ldcg(key + v);
+      const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
+      unsigned int m = __ballot_sync(0xffffffffu, active);
+      any |= (m != 0);
+      uint32_t r0 = 0, r1 = 0;
+      if (active) { r0 = rowptr[v]; r1 = rowptr[v + 1]; }
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned int kb = __shfl_sync(0xffffffffu, k, b);
+        const uint32_t e0 = __shfl_sync(0xffffffffu, r0, b), e1 = __shfl_sync(0xffffffffu, r1, b);
+        const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (kb & ((1u << kBfsRegionBits) - 1));
+        for (uint32_t e = e0 + lane; e < e1; e += 32) {
           const int w = tails[e];
           if (w < lnv && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
         }
