@@ -877,6 +877,184 @@ __global__ void __launch_bounds__(kTileV, 4) k_scan_rc(const ScanParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Scan kernel, fourth generation ("warp-synchronous loops").  Same tiles and phase A as k_scan.  Profiling k_scan
+// once the layout had locality showed it issue-bound at 12 of 32 lanes active: in the in-place reduction every
+// lane starts its inner "count this community" loop at a different moment, so the warp serialises them.  Here
+// phase B is arranged so that the lanes of a warp run the same loop at the same time:
+//   pass 0   counter[0] = weight towards the own community (one uniform walk over the staged segment);
+//   pass 1   repeat { every lane skips to its next not-yet-counted neighbour community; all lanes count their
+//            community together (one walk over the rest of the segment, marking duplicates); the community degree
+//            gather issued before the walk is consumed after it; gain + selection on registers }.
+// The trip count of the outer loop is the largest number of distinct neighbour communities among the warp's 32
+// vertices (about 4 after the first iterations) instead of the sum of all lanes' loops.  Sums are accumulated in
+// edge order per community, exactly like k_scan, so the weighted path keeps the reference's rounding.
+// ----------------------------------------------------------------------------------------------
+template <bool UNIT, bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);
+  double *s_w = reinterpret_cast<double *>(smem_raw + sizeof(int32_t) * kECap);
+  __shared__ int s_next, s_end, s_skip;
+  __shared__ uint32_t s_e0;
+  __shared__ unsigned long long s_red[3][kTileV / 32];
+  __shared__ double s_redd[kTileV / 32];
+
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileV;
+  const int v1 = min(p.lnv, v0 + kTileV);
+  const int v = v0 + tid;
+  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
+  uint32_t r0 = 0, r1 = 0;
+  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
+  const uint32_t deg = r1 - r0;
+  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
+  unsigned long long acc_le_u = 0, acc_moved = 0, acc_hash = 0;
+  double acc_le_d = 0.0;
+
+  int start = v0;
+  while (start < v1) {
+    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; }
+    __syncthreads();
+    if (s_skip) { start++; __syncthreads(); continue; }
+    const uint32_t E0 = s_e0;
+    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
+    __syncthreads();
+    const int end = s_end;
+    if (tid == end - 1 - v0) s_next = (int)r1;
+    __syncthreads();
+    const int ne = (int)((uint32_t)s_next - E0);
+
+    // ---- phase A
+    {
+      const int32_t *tl = p.tails + E0;
+      int i = tid;
+      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
+        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
+                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
+        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
+        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      }
+      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
+      if (!UNIT) {
+        const double *wl = p.weights + E0;
+        for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B: all 32 lanes of a warp walk their segments in lock step
+    const bool mine = (v >= start && v < end);
+    const int d = mine ? (int)deg : 0;
+    const int o0 = mine ? (int)(r0 - E0) : 0;
+    int cc = 0, best = 0;
+    if (mine) { cc = __ldg(p.cur + v); best = cc; }
+    int owner = 0; long long idx = 0;
+    double cc_deg = 0.0, vdeg = 0.0, sl = 0.0;
+    if (d) {
+      locate<MULTI>(p.pt, p.base, cc, owner, idx);
+      if (UNIT) {
+        cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+        vdeg = (double)d;
+        sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
+      } else {
+        cc_deg = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->degree);
+        vdeg = __ldg(p.vdeg + v);
+        sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
+      }
+    }
+    // pass 0: weight towards the own community, in edge order (counter[0], dspl.hpp:312-318)
+    double w0 = 0.0;
+    int cnt0 = 0;
+    for (int k = 0; k < d; k++) {
+      if (s_comm[o0 + k] == cc) { if (UNIT) cnt0++; else w0 += s_w[o0 + k]; }
+    }
+    if (UNIT) w0 = (double)cnt0;
+    const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
+    if (d) { if (UNIT) acc_le_u += (unsigned long long)cnt0; else acc_le_d += w0; }
+    // pass 1: one distinct neighbour community per lane per round
+    double bg = 0.0;
+    int lbest = kNoLabel;
+    int k = 0;
+    for (;;) {
+      while (k < d) { const int x = s_comm[o0 + k]; if (x == cc || x < 0) k++; else break; }
+      const bool has = k < d;
+      if (!__any_sync(0xffffffffu, has)) break;
+      int ck = 0, yo = 0; long long yi = 0;
+      double ay = 0.0, sum = 0.0;
+      if (has) {
+        ck = s_comm[o0 + k];
+        locate<MULTI>(p.pt, p.base, ck, yo, yi);
+        if (UNIT) ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+        else ay = __ldg(&((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi)->degree);
+        sum = UNIT ? 1.0 : s_w[o0 + k];
+      }
+      int c = 1;
+      for (int j = k + 1; j < d; j++) {                    // d == 0 / !has lanes fall through (k >= d)
+        if (has && s_comm[o0 + j] == ck) {
+          if (UNIT) c++; else sum += s_w[o0 + j];
+          s_comm[o0 + j] = -1;
+        }
+      }
+      if (has) {
+        if (UNIT) sum = (double)c;
+        const double g = gain_of(sum, eix, vdeg, ay, ax, p.constant);
+        if (better_l<MULTI>(p, g, ck, bg, best, lbest)) { bg = g; best = ck; }
+        k++;
+      }
+    }
+    if (mine) {
+      if (d && label_greater<MULTI>(p, best, lbest, cc)) {                   // singleton veto, dspl.hpp:224-225
+        int bo; long long bi;
+        locate<MULTI>(p.pt, p.base, best, bo, bi);
+        long long sz_cc, sz_b;
+        if (UNIT) {
+          sz_cc = __ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
+          sz_b = __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi);
+        } else {
+          sz_cc = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->size);
+          sz_b = __ldg(&((MULTI ? p.pt.cinfo_w[bo] : p.pt.cinfo_w[0]) + bi)->size);
+        }
+        if (sz_cc == 1 && sz_b == 1) best = cc;
+      }
+      if (best != cc) {                                                      // dspl.hpp:331-399
+        if (UNIT) push_move_unit<MULTI>(p, cc, best, d);
+        else push_move_w<MULTI>(p, cc, best, vdeg);
+      }
+      st_pol(p.tgt + v, best, pol_str);                                      // dspl.hpp:404
+      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
+    }
+    start = end;
+    __syncthreads();
+  }
+
+  const int lane = tid & 31, wid = tid >> 5;
+  if (UNIT) { const unsigned long long s = warp_sum(acc_le_u); if (lane == 0) s_red[0][wid] = s; }
+  else { const double s = warp_sum(acc_le_d); if (lane == 0) s_redd[wid] = s; }
+  if (TRACE) {
+    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
+    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (UNIT) {
+      unsigned long long s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
+      if (s) atomicAdd(&p.acc->le_u, s);
+    } else {
+      double s = 0;
+      for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
+      if (s != 0.0) atomicAdd(&p.acc->le_d, s);
+    }
+    if (TRACE) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
+      atomicAdd(&p.acc->moved, a);
+      atomicAdd(&p.acc->hash, b);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // High-degree vertices (degree > heavy_deg): one CTA per vertex, open-addressing table in HBM
 // scratch (2x degree entries) keyed by neighbour community; same decision rule.  Weighted sums are
 // accumulated with fp64 atomics here (order not fixed: weighted parity is tolerance-based anyway).

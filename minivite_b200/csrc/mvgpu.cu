@@ -131,7 +131,7 @@ struct mvgpu_ctx {
   bool peers_ready = false;
   int peers_unit = -1;
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 0, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -265,12 +265,14 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
     CK(cudaFuncSetAttribute(k_scan<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (UNIT) CK(cudaFuncSetAttribute(k_scan_fast<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_scan_rc<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_scan_ws<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
   if (tiles > 0) {
     if (UNIT && c->opt_scan_variant == 1) k_scan_fast<MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     else if (c->opt_scan_variant == 2) k_scan_rc<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    else if (c->opt_scan_variant == 3) k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
     else k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   }
