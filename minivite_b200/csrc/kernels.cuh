@@ -120,6 +120,9 @@ __device__ __forceinline__ void st_pol(int32_t *p, int v, unsigned long long pol
 template <bool MULTI>
 __device__ __forceinline__ void locate(const PeerTable &pt, long long base, int y, int &owner, long long &idx) {
   if (!MULTI) { owner = 0; idx = (long long)y - base; return; }
+  // almost every community a vertex meets is owned by its own rank: test that range first
+  const long long lo = pt.parts[pt.rank], hi = pt.parts[pt.rank + 1];
+  if ((long long)y >= lo && (long long)y < hi) { owner = pt.rank; idx = (long long)y - lo; return; }
   int o = 0;
 #pragma unroll 1
   while (o + 1 < pt.nranks && (long long)y >= pt.parts[o + 1]) o++;
@@ -1045,6 +1048,165 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
       for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
       if (s != 0.0) atomicAdd(&p.acc->le_d, s);
     }
+    if (TRACE) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
+      atomicAdd(&p.acc->moved, a);
+      atomicAdd(&p.acc->hash, b);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Unit-weight scan kernel, fifth generation ("private hash tables").  k_scan_ws is still issue-bound: its outer
+// loop runs max-over-lanes(distinct communities) rounds and every round walks the rest of the segment.  Here each
+// thread owns a kHtSlots-entry open-addressing table in shared memory (column-major: slot h of thread t lives at
+// [h][t], so a warp never has bank conflicts whatever slots its lanes probe) and makes ONE pass over its staged
+// neighbours: O(d) probes instead of O(rounds x d) compares.  A bit mask of occupied slots drives the gain loop.
+// Vertices with more distinct neighbour communities than slots are queued and handled by the in-place reduction.
+// ----------------------------------------------------------------------------------------------
+constexpr int kHtSlots = 16;
+
+template <bool MULTI, bool TRACE>
+__global__ void __launch_bounds__(kTileV) k_scan_ht(const ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);                 // kECap staged communities
+  int32_t *s_key = s_comm + kECap;                                         // [kHtSlots][kTileV]
+  int32_t *s_val = s_key + kHtSlots * kTileV;                              // [kHtSlots][kTileV]; doubles as s_cnt for the slow path
+  __shared__ int s_next, s_nslow, s_end, s_skip;
+  __shared__ uint32_t s_e0;
+  __shared__ int s_slow[kTileV];
+  __shared__ unsigned long long s_red[3][kTileV / 32];
+
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * kTileV;
+  const int v1 = min(p.lnv, v0 + kTileV);
+  const int v = v0 + tid;
+  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
+  uint32_t r0 = 0, r1 = 0;
+  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
+  const uint32_t deg = r1 - r0;
+  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
+  unsigned long long acc_le = 0, acc_moved = 0, acc_hash = 0;
+
+  int start = v0;
+  while (start < v1) {
+    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
+#pragma unroll
+    for (int h = 0; h < kHtSlots; h++) s_key[h * kTileV + tid] = -1;       // clear my table
+    __syncthreads();
+    if (s_skip) { start++; __syncthreads(); continue; }
+    const uint32_t E0 = s_e0;
+    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
+    __syncthreads();
+    const int end = s_end;
+    if (tid == end - 1 - v0) s_next = (int)r1;
+    __syncthreads();
+    const int ne = (int)((uint32_t)s_next - E0);
+
+    // ---- phase A
+    {
+      const int32_t *tl = p.tails + E0;
+      int i = tid;
+      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
+        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
+                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
+        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
+        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      }
+      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
+    }
+    __syncthreads();
+
+    // ---- phase B: one pass, private hash table
+    const bool mine = (v >= start && v < end);
+    const int d = mine ? (int)deg : 0;
+    const int o0 = mine ? (int)(r0 - E0) : 0;
+    int cc = 0, best = 0;
+    if (mine) { cc = __ldg(p.cur + v); best = cc; }
+    int owner = 0; long long idx = 0;
+    double cc_deg = 0.0;
+    if (d) {
+      locate<MULTI>(p.pt, p.base, cc, owner, idx);
+      cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+    }
+    int cnt0 = 0, nd = 0;
+    unsigned int occ = 0;
+    bool overflow = false;
+    int32_t *my_key = s_key + tid, *my_val = s_val + tid;
+    for (int k = 0; k < d; k++) {
+      const int c = s_comm[o0 + k];
+      if (c == cc) { cnt0++; continue; }
+      unsigned int h = ((unsigned int)c * 0x9E3779B1u) >> (32 - 4);
+      bool placed = false;
+#pragma unroll 1
+      for (int probe = 0; probe < kHtSlots; probe++) {
+        const int key = my_key[h * kTileV];
+        if (key == c) { my_val[h * kTileV]++; placed = true; break; }
+        if (key == -1) { my_key[h * kTileV] = c; my_val[h * kTileV] = 1; occ |= 1u << h; nd++; placed = true; break; }
+        h = (h + 1) & (kHtSlots - 1);
+      }
+      if (!placed) { overflow = true; break; }
+    }
+    bool done = mine;
+    if (overflow) { done = false; s_slow[atomicAdd(&s_nslow, 1)] = tid; }
+    else if (d) {
+      const double vdeg = (double)d;
+      const double sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
+      const double eix = __dsub_rn((double)cnt0, sl), ax = __dsub_rn(cc_deg, vdeg);
+      acc_le += (unsigned long long)cnt0;
+      double bg = 0.0;
+      int lbest = kNoLabel;
+      while (occ) {
+        const int h = __ffs(occ) - 1;
+        occ &= occ - 1;
+        const int y = my_key[h * kTileV];
+        int yo; long long yi;
+        locate<MULTI>(p.pt, p.base, y, yo, yi);
+        const double ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+        const double g = gain_of((double)my_val[h * kTileV], eix, vdeg, ay, ax, p.constant);
+        if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
+      }
+      if (label_greater<MULTI>(p, best, lbest, cc)) {                        // singleton veto, dspl.hpp:224-225
+        int bo; long long bi;
+        locate<MULTI>(p.pt, p.base, best, bo, bi);
+        if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 && __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
+          best = cc;
+      }
+      if (best != cc) push_move_unit<MULTI>(p, cc, best, d);                 // dspl.hpp:331-399
+    }
+    if (done) {
+      st_pol(p.tgt + v, best, pol_str);                                      // dspl.hpp:404
+      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
+    }
+    __syncthreads();
+    // ---- overflowed vertices: in-place reduction (uses s_val as the count array), packed into the first warps
+    const int nslow = s_nslow;
+    for (int q = tid; q < nslow; q += kTileV) {
+      const int sv = v0 + s_slow[q];
+      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
+      const int scc = __ldg(p.cur + sv);
+      const int sd = (int)(sr1 - sr0);
+      const int sbest = slow_vertex_unit<MULTI>(p, s_comm, s_val, (int)(sr0 - E0), sd, sv, scc, acc_le);
+      if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
+      p.tgt[sv] = sbest;
+      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
+    }
+    start = end;
+    __syncthreads();
+  }
+
+  const int lane = tid & 31, wid = tid >> 5;
+  { const unsigned long long s = warp_sum(acc_le); if (lane == 0) s_red[0][wid] = s; }
+  if (TRACE) {
+    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
+    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long s = 0;
+    for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
+    if (s) atomicAdd(&p.acc->le_u, s);
     if (TRACE) {
       unsigned long long a = 0, b = 0;
       for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }

@@ -266,13 +266,17 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
     if (UNIT) CK(cudaFuncSetAttribute(k_scan_fast<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_scan_rc<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_scan_ws<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (UNIT) CK(cudaFuncSetAttribute(k_scan_ht<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(int32_t) * (kECap + 2 * kHtSlots * kTileV))));
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
   if (tiles > 0) {
     if (UNIT && c->opt_scan_variant == 1) k_scan_fast<MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     else if (c->opt_scan_variant == 2) k_scan_rc<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
-    else if (c->opt_scan_variant == 3) k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
+    else if (c->opt_scan_variant == 4 && UNIT)
+      k_scan_ht<MULTI, TRACE><<<tiles, kTileV, sizeof(int32_t) * (kECap + 2 * kHtSlots * kTileV), c->stream>>>(sp);
+    else if (c->opt_scan_variant == 3 || c->opt_scan_variant == 4) k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
     else k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   }
