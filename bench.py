@@ -235,6 +235,7 @@ def main():
         return float(t.item())
 
     # ---- synthetic input: this rank's strip of the N-strip RGG (exact reference graph)
+    hg.set_num_threads(max(1, host_cores() // max(world, 1)))
     t0 = time.time()
     ss = hg.generate_rgg(nv_total, N, rank, rank + 1)
     sh = ss.shards[0]

@@ -22,6 +22,10 @@ extern "C" {
 
 const char *mvh_last_error() { return g_err.c_str(); }
 
+// OpenMP width of the host tools (launchers such as torchrun export OMP_NUM_THREADS=1)
+void mvh_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int mvh_get_max_threads() { return omp_get_max_threads(); }
+
 // Shards [r_begin, r_end) of the nprocs-strip RGG; r_end < 0 means all.
 int mvh_rgg_generate(int64_t nv, int nprocs, int r_begin, int r_end, int is_lcg, int unit_weight,
                      double random_edge_percent, void **out) {

@@ -1635,6 +1635,102 @@ __global__ void __launch_bounds__(256) k_final_labels(int lnv, const int32_t *cu
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Peer-memory collectives (comm_mode 1).  On one NVSwitch box every rank can store into every other rank's HBM,
+// so the three per-iteration exchanges of the Louvain loop need no library round trips:
+//   k_push_ghosts   my vertices' new communities are stored straight into the ghost tail of each peer's community
+//                   array (the all-to-all-v of dspl.hpp:559-646 as NVLink stores from the producing GPU);
+//   k_p2p_barrier   "every scan (and its remote atomics / ghost stores) has finished" before any fold;
+//   k_p2p_allreduce the two modularity partial sums (MPI_Allreduce, dspl.hpp:441) plus the trace counters: every
+//                   rank stores its contribution into every peer's mailbox, then each rank adds the mailbox up
+//                   in rank order (bit-identical on all ranks); doubles as the barrier before the next scan.
+// Synchronisation is an epoch counter per (destination, source) pair, written with st.release.sys after a
+// system-scope fence and polled with ld.acquire.sys; epochs only grow, so a fast peer can never be missed.
+// A watchdog turns a missing peer into an error flag instead of a hang.
+// ----------------------------------------------------------------------------------------------
+struct P2PState {                                   // one per rank, peer-mapped
+  unsigned long long arrive[kMaxRanks];             // [src] = last epoch src announced to me
+  unsigned long long vals[2][kMaxRanks][4];         // [epoch parity][src] = {le bits, la2 bits, moved, hash}
+  unsigned int error;
+  unsigned int pad_;
+};
+struct P2PPeers {
+  int rank, nranks;
+  P2PState *st[kMaxRanks];
+};
+struct PushTable {
+  int nranks;
+  long long soff[kMaxRanks + 1];                    // my send list, grouped by destination rank
+  int32_t *dst[kMaxRanks];                          // where my values start in that rank's target array
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_wait(P2PState *mine, int src, unsigned long long epoch) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(&mine->arrive[src]) < epoch) {
+    if (clock64() - t0 > 40000000000LL) { mine->error = 1; break; }     // ~20 s at 2 GHz: peer is gone
+  }
+}
+
+__global__ void __launch_bounds__(256) k_push_ghosts(const int32_t *comm, const int32_t *send_lid, long long nsend, PushTable t) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nsend; i += (long long)gridDim.x * blockDim.x) {
+    int q = 0;
+    while (i >= t.soff[q + 1]) q++;
+    t.dst[q][i - t.soff[q]] = comm[send_lid[i]];
+  }
+}
+
+__global__ void k_p2p_barrier(P2PPeers pp, unsigned long long epoch) {
+  const int t = threadIdx.x;
+  P2PState *mine = pp.st[pp.rank];
+  if (t < pp.nranks && t != pp.rank) {
+    __threadfence_system();
+    st_release_sys(&pp.st[t]->arrive[pp.rank], epoch);
+    p2p_wait(mine, t, epoch);
+  }
+}
+
+__global__ void k_p2p_allreduce(P2PPeers pp, unsigned long long epoch, const Acc *acc, int unit, double *out2,
+                                unsigned long long *tr2) {
+  const int t = threadIdx.x;
+  P2PState *mine = pp.st[pp.rank];
+  const int par = (int)(epoch & 1);
+  if (t < pp.nranks) {
+    const double le = unit ? (double)acc->le_u : acc->le_d, la2 = unit ? (double)acc->la2_u : acc->la2_d;
+    unsigned long long *dst = pp.st[t]->vals[par][pp.rank];
+    dst[0] = (unsigned long long)__double_as_longlong(le);
+    dst[1] = (unsigned long long)__double_as_longlong(la2);
+    dst[2] = acc->moved;
+    dst[3] = acc->hash;
+    if (t != pp.rank) {
+      __threadfence_system();
+      st_release_sys(&pp.st[t]->arrive[pp.rank], epoch);
+      p2p_wait(mine, t, epoch);
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    double e = 0.0, a = 0.0;
+    unsigned long long mv = 0, hs = 0;
+    for (int r = 0; r < pp.nranks; r++) {               // rank order: identical rounding on every rank
+      const volatile unsigned long long *v = mine->vals[par][r];
+      e += __longlong_as_double((long long)v[0]);
+      a += __longlong_as_double((long long)v[1]);
+      mv += v[2];
+      hs += v[3];
+    }
+    out2[0] = e; out2[1] = a;
+    tr2[0] = mv; tr2[1] = hs;
+  }
+}
+
 // ghost exchange helpers (dspl.hpp:559-571): pack the communities peers asked for; global -> local ids
 __global__ void __launch_bounds__(256) k_pack_send(const int32_t *comm, const int32_t *send_lid, int n, int32_t *out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = comm[send_lid[i]];

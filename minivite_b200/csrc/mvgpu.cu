@@ -66,8 +66,8 @@ struct DevBuf {              // grow-only device buffer (allocations are cached 
 };
 
 struct PeerBlob {            // what every rank publishes about its community arrays
-  cudaIpcMemHandle_t h[7];
-  unsigned long long raw[7];
+  cudaIpcMemHandle_t h[10];
+  unsigned long long raw[10];
   int pid, device, unit, pad;
 };
 
@@ -126,12 +126,18 @@ struct mvgpu_ctx {
   long long nheavy = 0, maxdeg = 0;
   int scan_has_self = 0, scan_heavy_deg = kECap;
   // peers
+  DevBuf<P2PState> p2p;
+  P2PPeers pp;
+  PushTable push[2];
+  unsigned long long p2p_epoch = 0;
+  bool p2p_zeroed = false;
+  int32_t *peer_comm[2][kMaxRanks];
   PeerTable pt;
   std::vector<void *> ipc_opened;
   bool peers_ready = false;
   int peers_unit = -1;
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -213,10 +219,11 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   c->ipc_opened.clear();
   PeerBlob mine;
   memset(&mine, 0, sizeof mine);
-  void *ptrs[7] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
+  void *ptrs[10] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
                    unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
-                   unit ? nullptr : (void *)c->udeg.p, c->relabel ? (void *)c->lab.p : nullptr};
-  for (int k = 0; k < 7; k++) {
+                   unit ? nullptr : (void *)c->udeg.p, c->relabel ? (void *)c->lab.p : nullptr,
+                   (void *)c->comm_a.p, (void *)c->comm_b.p, (void *)c->p2p.p};
+  for (int k = 0; k < 10; k++) {
     mine.raw[k] = (unsigned long long)ptrs[k];
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
   }
@@ -230,9 +237,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
   CK(cudaStreamSynchronize(c->stream));
   d_all.release();
   for (int r = 0; r < c->nranks; r++) {
-    void *q[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *q[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (all[r].unit != unit) return fail("ranks disagree on the unit-weight path");
-    if (r == c->rank) { for (int k = 0; k < 7; k++) q[k] = ptrs[k]; }
+    if (r == c->rank) { for (int k = 0; k < 10; k++) q[k] = ptrs[k]; }
     else if (all[r].pid == mine.pid) {           // same process (threads): plain UVA pointers + peer access
       int can = 0;
       CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
@@ -240,9 +247,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
       cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
       cudaGetLastError();
-      for (int k = 0; k < 7; k++) q[k] = (void *)all[r].raw[k];
+      for (int k = 0; k < 10; k++) q[k] = (void *)all[r].raw[k];
     } else {
-      for (int k = 0; k < 7; k++)
+      for (int k = 0; k < 10; k++)
         if (all[r].raw[k]) {
           CK(cudaIpcOpenMemHandle(&q[k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess));
           c->ipc_opened.push_back(q[k]);
@@ -251,6 +258,28 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     pt.cdeg[r] = (const uint32_t *)q[0]; pt.csize[r] = (const int32_t *)q[1]; pt.upd[r] = (unsigned long long *)q[2];
     pt.cinfo_w[r] = (const CommW *)q[3]; pt.usize[r] = (long long *)q[4]; pt.udeg[r] = (double *)q[5];
     pt.lab[r] = (const int32_t *)q[6];
+    c->peer_comm[0][r] = (int32_t *)q[7]; c->peer_comm[1][r] = (int32_t *)q[8];
+    c->pp.st[r] = (P2PState *)q[9];
+  }
+  // where my send segments land in each peer's community array: its lnv + its receive offset for me
+  {
+    DevBuf<long long> d_gb;
+    TRY(d_gb.ensure((size_t)c->nranks * (c->nranks + 1)));
+    std::vector<long long> gb(c->nranks), allgb((size_t)c->nranks * c->nranks);
+    for (int r = 0; r < c->nranks; r++) gb[r] = c->lnv + c->roff[r];
+    long long *mine_d = d_gb.p + (size_t)c->nranks * c->nranks;
+    CK(cudaMemcpyAsync(mine_d, gb.data(), sizeof(long long) * c->nranks, cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.AllGather(mine_d, d_gb.p, c->nranks, ncclInt64, c->comm, c->stream));
+    CK(cudaMemcpyAsync(allgb.data(), d_gb.p, sizeof(long long) * allgb.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    d_gb.release();
+    for (int b = 0; b < 2; b++) {
+      PushTable &t = c->push[b];
+      t.nranks = c->nranks;
+      for (int r = 0; r <= c->nranks; r++) t.soff[r] = c->soff[r];
+      for (int r = 0; r < c->nranks; r++) t.dst[r] = c->peer_comm[b][r] + allgb[(size_t)r * c->nranks + c->rank];
+    }
+    c->pp.rank = c->rank; c->pp.nranks = c->nranks;
   }
   c->peers_ready = true;
   c->peers_unit = unit * 2 + c->relabel;
@@ -554,6 +583,10 @@ int setup_run(mvgpu_ctx *c) {
     TRY(c->hkeys.ensure(off[c->nheavy]));
     if (c->unit) TRY(c->hvals_i.ensure(off[c->nheavy])); else TRY(c->hvals_d.ensure(off[c->nheavy]));
   }
+  if (c->nranks > 1) {
+    TRY(c->p2p.ensure(1));
+    if (!c->p2p_zeroed) { CK(cudaMemsetAsync(c->p2p.p, 0, sizeof(P2PState), s)); CK(cudaStreamSynchronize(s)); c->p2p_zeroed = true; }
+  }
   TRY(setup_peers(c, c->unit ? 1 : 0));
   c->tm.unit_weight = c->unit ? 1 : 0;
   c->scan_has_self = has_self;
@@ -609,7 +642,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   sp.pt = c->pt;
   c->last_sp = sp;
 
-  struct HostMail { Acc acc; double red2[2]; unsigned long long tr2[2]; };
+  struct HostMail { Acc acc; double red2[2]; unsigned long long tr2[2]; unsigned int p2p_error; };
   HostMail *mail = reinterpret_cast<HostMail *>(c->h_pin);
   const size_t ev_iter0 = ev;
   double prevMod = lower, currMod = -1.0;
@@ -624,11 +657,21 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     CK(cudaEventRecord(e0, s));
     TRY(launch_scan(c, sp));
     CK(cudaEventRecord(e1, s));
+    const bool p2p = c->nranks > 1 && c->opt_comm_mode == 1;
     if (c->nranks > 1) {
-      // ghost values of the NEW assignment go into tgt's ghost tail; the all-reduce doubles as the
-      // "every scan has finished" barrier that must precede any fold (remote atomics / reads).
-      TRY(exchange_ghosts(c, tgt));
-      NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclSum, c->comm, s));
+      // ghost values of the NEW assignment go into the ghost tail of every peer's tgt array; then "every scan has
+      // finished" (its remote atomics and ghost stores included) must hold before any rank folds.
+      if (p2p) {
+        if (c->nsend) {
+          k_push_ghosts<<<grid_for(c->nsend, 256, c->num_sms), 256, 0, s>>>(tgt, c->send_lid.p, c->nsend, c->push[tgt == c->comm_b.p ? 1 : 0]);
+          c->tm.kernel_launches++;
+        }
+        k_p2p_barrier<<<1, 32, 0, s>>>(c->pp, ++c->p2p_epoch);
+        c->tm.kernel_launches++;
+      } else {
+        TRY(exchange_ghosts(c, tgt));
+        NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclSum, c->comm, s));
+      }
     }
     CK(cudaEventRecord(e2, s));
     if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, acc);
@@ -637,7 +680,16 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     CK(cudaEventRecord(e3, s));
     double e_xx, a2_x;
     unsigned long long moved = 0, hash = 0;
-    if (c->nranks > 1) {
+    if (p2p) {
+      k_p2p_allreduce<<<1, 32, 0, s>>>(c->pp, ++c->p2p_epoch, acc, c->unit ? 1 : 0, d_sc->red2, d_sc->tr2);   // dspl.hpp:441
+      c->tm.kernel_launches++;
+      CK(cudaMemcpyAsync(mail->red2, d_sc->red2, sizeof mail->red2 + sizeof mail->tr2, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(&mail->p2p_error, &c->p2p.p->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (mail->p2p_error) return fail("peer-memory collective timed out (a peer rank is gone)");
+      e_xx = mail->red2[0]; a2_x = mail->red2[1];
+      moved = mail->tr2[0]; hash = mail->tr2[1];
+    } else if (c->nranks > 1) {
       k_acc_to_double<<<1, 32, 0, s>>>(acc, c->unit ? 1 : 0, d_sc->red2);
       c->tm.kernel_launches++;
       NK(g_nccl.AllReduce(d_sc->red2, d_sc->red2, 2, ncclDouble, ncclSum, c->comm, s));   // dspl.hpp:441
@@ -753,6 +805,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->bfs_key.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
   c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
   c->weights2.release(); c->level_flags.release();
+  c->p2p.release();
   c->send_lid.release(); c->send_buf.release(); c->heavy_list.release(); c->hkeys.release(); c->hvals_i.release();
   c->hvals_d.release(); c->heavy_off.release();
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -862,6 +915,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "scan_variant") c->opt_scan_variant = (int)value;
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else if (n == "reorder") c->opt_reorder = (int)value;
+  else if (n == "comm_mode") c->opt_comm_mode = (int)value;
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;

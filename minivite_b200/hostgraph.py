@@ -34,8 +34,14 @@ def lib():
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
         L.mvh_graph_write.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.mvh_graph_free.argtypes = [ctypes.c_void_p]
+        L.mvh_set_num_threads.argtypes = [ctypes.c_int]
         _lib = L
     return _lib
+
+
+def set_num_threads(n):
+    """OpenMP width of the host-side generator (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().mvh_set_num_threads(int(n))
 
 
 def _check(rc):

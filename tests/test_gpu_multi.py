@@ -109,6 +109,18 @@ def test_multi_gpu_with_renumbering(tmp_path, golden):
     check(res, golden["rgg_n16384_p2"])
 
 
+def test_multi_gpu_nccl_collectives_mode(tmp_path, golden):
+    """comm_mode=0: the per-iteration exchanges go through NCCL (grouped send/recv all-to-all-v + all-reduce)
+    instead of peer-memory stores; results are identical."""
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    for name in ("rgg_n16384_p2", "hand_clique_ring_p2"):
+        res = run_ranks(tmp_path, 2, name, comm_mode=0)
+        check(res, golden[name])
+        res = run_ranks(tmp_path, 2, name, comm_mode=0, reorder=1, region_size=64)
+        check(res, golden[name])
+
+
 def test_multi_gpu_weighted_and_heavy(tmp_path, golden):
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
