@@ -94,8 +94,7 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
 /* Options: "trace" (0/1: record moved/chash per iteration, default 0), "max_iters" (safety cap,
  * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
- * "scan_variant" (3 = warp-synchronous loops (default), 0 = first generic kernel, 1 = register sorting network,
- * 2 = register cache; all give identical results),
+ * "scan_variant" (3 = warp-synchronous loops (default), 0 = first kernel; identical results),
  * "cache_policy" (bit0 evict_last on community gathers, bit1 evict_last on degree gathers, bit2 evict_first on
  * streamed arrays; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target

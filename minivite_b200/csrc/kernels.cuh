@@ -74,6 +74,14 @@ struct ScanParams {
   int32_t *hkeys;
   double *hvals_d;
   int32_t *hvals_i;
+  // this rank's own community arrays (the common case: no indexed constant-bank load)
+  const uint32_t *loc_cdeg;
+  const int32_t *loc_csize;
+  unsigned long long *loc_upd;
+  const CommW *loc_cinfo_w;
+  long long *loc_usize;
+  double *loc_udeg;
+  const int32_t *loc_lab;
   PeerTable pt;
 };
 
@@ -130,6 +138,20 @@ __device__ __forceinline__ void locate(const PeerTable &pt, long long base, int 
   idx = (long long)y - pt.parts[o];
 }
 
+#define MV_PTR(field, type)                                                                          \
+  template <bool MULTI>                                                                              \
+  __device__ __forceinline__ type ptr_##field(const ScanParams &p, int o) {                          \
+    return (!MULTI || o == p.pt.rank) ? p.loc_##field : p.pt.field[o];                               \
+  }
+MV_PTR(cdeg, const uint32_t *)
+MV_PTR(csize, const int32_t *)
+MV_PTR(upd, unsigned long long *)
+MV_PTR(cinfo_w, const CommW *)
+MV_PTR(usize, long long *)
+MV_PTR(udeg, double *)
+MV_PTR(lab, const int32_t *)
+#undef MV_PTR
+
 __device__ __forceinline__ unsigned long long pack_delta(int dsize, long long ddeg) {
   return (unsigned long long)(((long long)dsize << 32) + ddeg);
 }
@@ -155,7 +177,7 @@ __device__ __forceinline__ int label_of(const ScanParams &p, int c) {
   if (!p.relabel) return c;
   int o; long long i;
   locate<MULTI>(p.pt, p.base, c, o, i);
-  return __ldg((MULTI ? p.pt.lab[o] : p.pt.lab[0]) + i);
+  return __ldg(ptr_lab<MULTI>(p, o) + i);
 }
 // better() with lazily fetched labels; lby caches the label of the current best (kNoLabel = not fetched)
 template <bool MULTI>
@@ -285,8 +307,8 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
               if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
             s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
           }
-          cc_size = (long long)__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
-          cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+          cc_size = (long long)__ldg(ptr_csize<MULTI>(p, owner) + idx);
+          cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
           vdeg = (double)d;
           const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
           eix = (double)(cnt0 - sl);
@@ -302,7 +324,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
               if (s_comm[o0 + j] == ck) { sum += s_w[o0 + j]; s_comm[o0 + j] = -1; }
             s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
           }
-          const CommW *cw = (MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx;
+          const CommW *cw = ptr_cinfo_w<MULTI>(p, owner) + idx;
           const double2 raw = __ldg(reinterpret_cast<const double2 *>(cw));
           cc_size = __double_as_longlong(raw.x);
           cc_deg = raw.y;
@@ -321,11 +343,11 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
           locate<MULTI>(p.pt, p.base, y, yo, yi);
           double ay, eiy; long long ysize;
           if (UNIT) {
-            ysize = (long long)__ldg((MULTI ? p.pt.csize[yo] : p.pt.csize[0]) + yi);
-            ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+            ysize = (long long)__ldg(ptr_csize<MULTI>(p, yo) + yi);
+            ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
             eiy = (double)s_cnt[o0 + m];
           } else {
-            const double2 raw = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi));
+            const double2 raw = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, yo) + yi));
             ysize = __double_as_longlong(raw.x);
             ay = raw.y;
             eiy = s_w[o0 + m];
@@ -338,13 +360,13 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
           int bo; long long bi;
           locate<MULTI>(p.pt, p.base, best, bo, bi);
           if (UNIT) {
-            atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)d));
-            atomicAdd((MULTI ? p.pt.upd[owner] : p.pt.upd[0]) + idx, pack_delta(-1, -(long long)d));
+            atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
+            atomicAdd(ptr_upd<MULTI>(p, owner) + idx, pack_delta(-1, -(long long)d));
           } else {
-            atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
-            atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
-            atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[owner] : p.pt.usize[0]) + idx), ~0ULL);
-            atomicAdd((MULTI ? p.pt.udeg[owner] : p.pt.udeg[0]) + idx, -vdeg);
+            atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
+            atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
+            atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, owner) + idx), ~0ULL);
+            atomicAdd(ptr_udeg<MULTI>(p, owner) + idx, -vdeg);
           }
         }
       }
@@ -383,31 +405,14 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
   }
 }
 
-// ----------------------------------------------------------------------------------------------
-// Unit-weight scan kernel, second generation.  Same tile/sub-range structure and phase A as k_scan;
-// phase B keeps a vertex's (<= kFastDeg) staged neighbour communities in REGISTERS:
-//   * Batcher odd-even merge sorting network (63 compare-exchanges, no divergence, no shared-memory
-//     traffic) -> equal communities become adjacent; run lengths are the per-community edge counts
-//     (counter[] of dspl.hpp:262-270 for unit weights);
-//   * the <= 16 degree gathers of the distinct neighbour communities are issued back to back
-//     (memory-level parallelism instead of a dependent chain), then the gains (dspl.hpp:212) and the
-//     (gain desc, id asc) selection (dspl.hpp:214-219) run on registers;
-//   * community sizes are only read when the singleton veto (dspl.hpp:224-225) can fire.
-// Vertices with more than kFastDeg staged neighbours (5.6% on the benchmark RGG) are queued in shared
-// memory and handled afterwards by the generic in-place reduction, densely packed into few warps.
-// Cache policy: `cur` gathers evict_last, streamed tails / rowptr / target writes evict_first.
-// ----------------------------------------------------------------------------------------------
-constexpr int kFastDeg = 16;
-
-__device__ __forceinline__ void cmpx(int &a, int &b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
-
+// ---- helpers shared by the scan kernels ----------------------------------------------------------------
 template <bool MULTI>
 __device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
   int bo, co; long long bi, ci;
   locate<MULTI>(p.pt, p.base, best, bo, bi);
   locate<MULTI>(p.pt, p.base, cc, co, ci);
-  atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)d));
-  atomicAdd((MULTI ? p.pt.upd[co] : p.pt.upd[0]) + ci, pack_delta(-1, -(long long)d));
+  atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
+  atomicAdd(ptr_upd<MULTI>(p, co) + ci, pack_delta(-1, -(long long)d));
 }
 
 // generic in-place reduction of one vertex's staged segment (any degree <= kECap), unit weights
@@ -426,7 +431,7 @@ __device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_
   }
   int owner; long long idx;
   locate<MULTI>(p.pt, p.base, cc, owner, idx);
-  const double cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+  const double cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
   const double vdeg = (double)d;
   const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
   const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
@@ -437,199 +442,18 @@ __device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_
     const int y = s_comm[o0 + m];
     int yo; long long yi;
     locate<MULTI>(p.pt, p.base, y, yo, yi);
-    const double ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
+    const double ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
     const double g = gain_of((double)s_cnt[o0 + m], eix, vdeg, ay, ax, p.constant);
     if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
   }
   if (label_greater<MULTI>(p, best, lbest, cc)) {                            // dspl.hpp:224-225
     int bo; long long bi;
     locate<MULTI>(p.pt, p.base, best, bo, bi);
-    if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 && __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
+    if (__ldg(ptr_csize<MULTI>(p, owner) + idx) == 1 && __ldg(ptr_csize<MULTI>(p, bo) + bi) == 1)
       best = cc;
   }
   return best;
 }
-
-template <bool MULTI, bool TRACE>
-__global__ void __launch_bounds__(kTileV, 3) k_scan_fast(const ScanParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);     // kECap staged neighbour communities
-  int32_t *s_cnt = s_comm + kECap;                             // kECap counts (slow path only)
-  __shared__ int s_next, s_nslow, s_end, s_skip;
-  __shared__ uint32_t s_e0;
-  __shared__ int s_slow[kTileV];
-  __shared__ unsigned long long s_red[3][kTileV / 32];
-
-  const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * kTileV;
-  const int v1 = min(p.lnv, v0 + kTileV);
-  const int v = v0 + tid;
-  const unsigned long long pol_cur = make_policy((p.cache_policy & 1) ? 1 : 0);
-  const unsigned long long pol_deg = make_policy((p.cache_policy & 2) ? 1 : 0);
-  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
-  uint32_t r0 = 0, r1 = 0;
-  if (v < v1) { r0 = ld_pol(p.rowptr + v, pol_str); r1 = ld_pol(p.rowptr + v + 1, pol_str); }
-  const uint32_t deg = r1 - r0;
-  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
-  unsigned long long acc_le = 0, acc_moved = 0, acc_hash = 0;
-
-  int start = v0;
-  while (start < v1) {
-    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
-    __syncthreads();
-    if (s_skip) { start++; __syncthreads(); continue; }
-    const uint32_t E0 = s_e0;
-    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
-    __syncthreads();
-    const int end = s_end;
-    if (tid == end - 1 - v0) s_next = (int)r1;
-    __syncthreads();
-    const int ne = (int)((uint32_t)s_next - E0);
-
-    // ---- phase A: coalesced stream of tails, gather cur[tail] (evict_last), stage in shared memory
-    {
-      const int32_t *tl = p.tails + E0;
-      int i = tid;
-      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
-        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
-                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
-        const int c0 = ld_pol(p.cur + t0, pol_cur), c1 = ld_pol(p.cur + t1, pol_cur), c2 = ld_pol(p.cur + t2, pol_cur),
-                  c3 = ld_pol(p.cur + t3, pol_cur);
-        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
-      }
-      for (; i < ne; i += kTileV) s_comm[i] = ld_pol(p.cur + ld_pol_stream(tl + i, pol_str), pol_cur);
-    }
-    __syncthreads();
-
-    // ---- phase B (fast path): registers + sorting network
-    const bool mine = (v >= start && v < end);
-    int cc = 0, best = 0;
-    if (mine) {
-      cc = ld_pol(p.cur + v, pol_cur);
-      best = cc;
-      const int d = (int)deg;
-      if (d > kFastDeg) s_slow[atomicAdd(&s_nslow, 1)] = tid;
-      else if (d != 0) {
-        const int o0 = (int)(r0 - E0);
-        int a[kFastDeg];
-#pragma unroll
-        for (int k = 0; k < kFastDeg; k++) a[k] = (k < d) ? s_comm[o0 + k] : 0x7fffffff;
-        // Batcher odd-even merge sort for 16 keys, 63 compare-exchanges, written out (generated; verified with the
-        // 0/1 principle) so that every index is a literal and the keys stay in registers
-        cmpx(a[0], a[1]); cmpx(a[2], a[3]); cmpx(a[4], a[5]); cmpx(a[6], a[7]); cmpx(a[8], a[9]); cmpx(a[10], a[11]);
-        cmpx(a[12], a[13]); cmpx(a[14], a[15]); cmpx(a[0], a[2]); cmpx(a[1], a[3]); cmpx(a[4], a[6]); cmpx(a[5], a[7]);
-        cmpx(a[8], a[10]); cmpx(a[9], a[11]); cmpx(a[12], a[14]); cmpx(a[13], a[15]); cmpx(a[1], a[2]); cmpx(a[5], a[6]);
-        cmpx(a[9], a[10]); cmpx(a[13], a[14]); cmpx(a[0], a[4]); cmpx(a[1], a[5]); cmpx(a[2], a[6]); cmpx(a[3], a[7]);
-        cmpx(a[8], a[12]); cmpx(a[9], a[13]); cmpx(a[10], a[14]); cmpx(a[11], a[15]); cmpx(a[2], a[4]); cmpx(a[3], a[5]);
-        cmpx(a[10], a[12]); cmpx(a[11], a[13]); cmpx(a[1], a[2]); cmpx(a[3], a[4]); cmpx(a[5], a[6]); cmpx(a[9], a[10]);
-        cmpx(a[11], a[12]); cmpx(a[13], a[14]); cmpx(a[0], a[8]); cmpx(a[1], a[9]); cmpx(a[2], a[10]); cmpx(a[3], a[11]);
-        cmpx(a[4], a[12]); cmpx(a[5], a[13]); cmpx(a[6], a[14]); cmpx(a[7], a[15]); cmpx(a[4], a[8]); cmpx(a[5], a[9]);
-        cmpx(a[6], a[10]); cmpx(a[7], a[11]); cmpx(a[2], a[4]); cmpx(a[3], a[5]); cmpx(a[6], a[8]); cmpx(a[7], a[9]);
-        cmpx(a[10], a[12]); cmpx(a[11], a[13]); cmpx(a[1], a[2]); cmpx(a[3], a[4]); cmpx(a[5], a[6]); cmpx(a[7], a[8]);
-        cmpx(a[9], a[10]); cmpx(a[11], a[12]); cmpx(a[13], a[14]);
-        // run lengths: rl[k] = length of the run that ends at k (0 if k is not a run end)
-        int rl[kFastDeg];
-        int run = 0, cnt0 = 0;
-#pragma unroll
-        for (int k = 0; k < kFastDeg; k++) {
-          run++;
-          const bool endrun = (k == kFastDeg - 1) || (a[k] != a[k + 1]);
-          int r = endrun ? run : 0;
-          if (endrun) run = 0;
-          if (a[k] == 0x7fffffff) r = 0;                   // padding
-          if (a[k] == cc) { cnt0 += r; r = 0; }            // own community: counter[0]
-          rl[k] = r;
-        }
-        // degree gathers of the distinct neighbour communities, all in flight together
-        uint32_t dg[kFastDeg];
-#pragma unroll
-        for (int k = 0; k < kFastDeg; k++) {
-          dg[k] = 0;
-          if (rl[k]) {
-            int yo; long long yi;
-            locate<MULTI>(p.pt, p.base, a[k], yo, yi);
-            dg[k] = ld_pol((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi, pol_deg);
-          }
-        }
-        int owner; long long idx;
-        locate<MULTI>(p.pt, p.base, cc, owner, idx);
-        const double cc_deg = (double)ld_pol((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx, pol_deg);
-        const double vdeg = (double)d;
-        const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
-        const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
-        acc_le += (unsigned long long)cnt0;
-        double bg = 0.0;
-        int lbest = kNoLabel;
-#pragma unroll
-        for (int k = 0; k < kFastDeg; k++) {
-          if (rl[k]) {
-            const double g = gain_of((double)rl[k], eix, vdeg, (double)dg[k], ax, p.constant);
-            if (better_l<MULTI>(p, g, a[k], bg, best, lbest)) { bg = g; best = a[k]; }
-          }
-        }
-        if (label_greater<MULTI>(p, best, lbest, cc)) {                      // singleton veto, dspl.hpp:224-225
-          int bo; long long bi;
-          locate<MULTI>(p.pt, p.base, best, bo, bi);
-          if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 &&
-              __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
-            best = cc;
-        }
-        if (best != cc) push_move_unit<MULTI>(p, cc, best, d);               // dspl.hpp:331-399
-      }
-      if (d <= kFastDeg) {
-        st_pol(p.tgt + v, best, pol_str);                                    // dspl.hpp:404
-        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
-      }
-    }
-    __syncthreads();
-    // ---- phase B (slow path): queued larger vertices, one thread each, packed into the first warps
-    const int nslow = s_nslow;
-    for (int q = tid; q < nslow; q += kTileV) {
-      const int t = s_slow[q];
-      const int sv = v0 + t;
-      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
-      const int scc = __ldg(p.cur + sv);
-      const int sd = (int)(sr1 - sr0);
-      const int sbest = slow_vertex_unit<MULTI>(p, s_comm, s_cnt, (int)(sr0 - E0), sd, sv, scc, acc_le);
-      if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
-      p.tgt[sv] = sbest;
-      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
-    }
-    start = end;
-    __syncthreads();
-  }
-
-  const int lane = tid & 31, wid = tid >> 5;
-  { const unsigned long long s = warp_sum(acc_le); if (lane == 0) s_red[0][wid] = s; }
-  if (TRACE) {
-    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
-    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long s = 0;
-    for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
-    if (s) atomicAdd(&p.acc->le_u, s);
-    if (TRACE) {
-      unsigned long long a = 0, b = 0;
-      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
-      atomicAdd(&p.acc->moved, a);
-      atomicAdd(&p.acc->hash, b);
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
-// Scan kernel, third generation ("register cache"): same tiles and phase A as k_scan; in phase B each thread
-// walks its vertex's staged neighbours ONCE, in edge order, keeping up to kRcK distinct neighbour communities and
-// their weight sums in registers (straight-line compare/accumulate code, no inner search loop, no shared-memory
-// writes).  After the first few iterations almost every vertex sees only a handful of communities, so the
-// divergent O(d * distinct) in-place reduction of k_scan is replaced by O(d) uniform work; vertices that overflow
-// the cache (common only in iterations 1-3) are queued and reduced afterwards by the generic in-place code,
-// packed densely into the first warps.  Sums are accumulated sequentially in edge order, so this kernel also
-// serves the weighted (fp64) path with the reference's summation order.
-// ----------------------------------------------------------------------------------------------
-constexpr int kRcK = 6;
 
 // generic in-place reduction of one vertex's staged segment (any degree <= kECap), weighted
 template <bool MULTI>
@@ -648,7 +472,7 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
   }
   int owner; long long idx;
   locate<MULTI>(p.pt, p.base, cc, owner, idx);
-  const double2 raw = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx));
+  const double2 raw = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, owner) + idx));
   const long long cc_size = __double_as_longlong(raw.x);
   const double vdeg = __ldg(p.vdeg + v);
   vdeg_out = vdeg;
@@ -662,7 +486,7 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
     const int y = s_comm[o0 + m];
     int yo; long long yi;
     locate<MULTI>(p.pt, p.base, y, yo, yi);
-    const double2 ry = __ldg(reinterpret_cast<const double2 *>((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi));
+    const double2 ry = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, yo) + yi));
     const double g = gain_of(s_w[o0 + m], eix, vdeg, ry.y, ax, p.constant);
     if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; best_size = __double_as_longlong(ry.x); }
   }
@@ -675,212 +499,14 @@ __device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int bes
   int bo, co; long long bi, ci;
   locate<MULTI>(p.pt, p.base, best, bo, bi);
   locate<MULTI>(p.pt, p.base, cc, co, ci);
-  atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
-  atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
-  atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[co] : p.pt.usize[0]) + ci), ~0ULL);
-  atomicAdd((MULTI ? p.pt.udeg[co] : p.pt.udeg[0]) + ci, -vdeg);
-}
-
-template <bool UNIT, bool MULTI, bool TRACE>
-__global__ void __launch_bounds__(kTileV, 4) k_scan_rc(const ScanParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);
-  int32_t *s_cnt = s_comm + kECap;
-  double *s_w = reinterpret_cast<double *>(smem_raw + sizeof(int32_t) * kECap);
-  __shared__ int s_next, s_nslow, s_end, s_skip;
-  __shared__ uint32_t s_e0;
-  __shared__ int s_slow[kTileV];
-  __shared__ unsigned long long s_red[3][kTileV / 32];
-  __shared__ double s_redd[kTileV / 32];
-
-  const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * kTileV;
-  const int v1 = min(p.lnv, v0 + kTileV);
-  const int v = v0 + tid;
-  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
-  uint32_t r0 = 0, r1 = 0;
-  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
-  const uint32_t deg = r1 - r0;
-  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
-  unsigned long long acc_le_u = 0, acc_moved = 0, acc_hash = 0;
-  double acc_le_d = 0.0;
-
-  int start = v0;
-  while (start < v1) {
-    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
-    __syncthreads();
-    if (s_skip) { start++; __syncthreads(); continue; }
-    const uint32_t E0 = s_e0;
-    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
-    __syncthreads();
-    const int end = s_end;
-    if (tid == end - 1 - v0) s_next = (int)r1;
-    __syncthreads();
-    const int ne = (int)((uint32_t)s_next - E0);
-
-    // ---- phase A
-    {
-      const int32_t *tl = p.tails + E0;
-      int i = tid;
-      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
-        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
-                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
-        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
-        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
-      }
-      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
-      if (!UNIT) {
-        const double *wl = p.weights + E0;
-        for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
-      }
-    }
-    __syncthreads();
-
-    // ---- phase B, pass 1: register cache of distinct neighbour communities
-    if (v >= start && v < end) {
-      const int cc = __ldg(p.cur + v);
-      int best = cc;
-      bool done = true;
-      const int d = (int)deg;
-      if (d != 0) {
-        const int o0 = (int)(r0 - E0);
-        int ck[kRcK];
-        double nk[kRcK];                       // unit: exact small integers
-#pragma unroll
-        for (int i = 0; i < kRcK; i++) { ck[i] = -1; nk[i] = 0.0; }
-        int nd = 0;
-        double w0 = 0.0;
-        bool overflow = false;
-        for (int k = 0; k < d; k++) {
-          const int c = s_comm[o0 + k];
-          const double w = UNIT ? 1.0 : s_w[o0 + k];
-          if (c == cc) { w0 += w; continue; }
-          bool hit = false;
-#pragma unroll
-          for (int i = 0; i < kRcK; i++)
-            if (ck[i] == c) { nk[i] += w; hit = true; }
-          if (!hit) {
-            if (nd == kRcK) { overflow = true; break; }
-#pragma unroll
-            for (int i = 0; i < kRcK; i++)
-              if (i == nd) { ck[i] = c; nk[i] = w; }
-            nd++;
-          }
-        }
-        if (overflow) { done = false; s_slow[atomicAdd(&s_nslow, 1)] = tid; }
-        else {
-          int owner; long long idx;
-          locate<MULTI>(p.pt, p.base, cc, owner, idx);
-          double cc_deg, vdeg, sl;
-          if (UNIT) {
-            cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
-            vdeg = (double)d;
-            sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
-            acc_le_u += (unsigned long long)w0;
-          } else {
-            cc_deg = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->degree);
-            vdeg = __ldg(p.vdeg + v);
-            sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
-            acc_le_d += w0;
-          }
-          const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
-          double ay[kRcK];
-#pragma unroll
-          for (int i = 0; i < kRcK; i++) {
-            ay[i] = 0.0;
-            if (i < nd) {
-              int yo; long long yi;
-              locate<MULTI>(p.pt, p.base, ck[i], yo, yi);
-              if (UNIT) ay[i] = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
-              else ay[i] = __ldg(&((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi)->degree);
-            }
-          }
-          double bg = 0.0;
-          int lbest = kNoLabel;
-#pragma unroll
-          for (int i = 0; i < kRcK; i++) {
-            if (i < nd) {
-              const double g = gain_of(nk[i], eix, vdeg, ay[i], ax, p.constant);
-              if (better_l<MULTI>(p, g, ck[i], bg, best, lbest)) { bg = g; best = ck[i]; }
-            }
-          }
-          if (label_greater<MULTI>(p, best, lbest, cc)) {                    // singleton veto, dspl.hpp:224-225
-            int bo; long long bi;
-            locate<MULTI>(p.pt, p.base, best, bo, bi);
-            long long sz_cc, sz_b;
-            if (UNIT) {
-              sz_cc = __ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
-              sz_b = __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi);
-            } else {
-              sz_cc = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->size);
-              sz_b = __ldg(&((MULTI ? p.pt.cinfo_w[bo] : p.pt.cinfo_w[0]) + bi)->size);
-            }
-            if (sz_cc == 1 && sz_b == 1) best = cc;
-          }
-          if (best != cc) {                                                  // dspl.hpp:331-399
-            if (UNIT) push_move_unit<MULTI>(p, cc, best, d);
-            else push_move_w<MULTI>(p, cc, best, vdeg);
-          }
-        }
-      }
-      if (done) {
-        st_pol(p.tgt + v, best, pol_str);                                    // dspl.hpp:404
-        if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
-      }
-    }
-    __syncthreads();
-    // ---- phase B, pass 2: cache overflows, generic in-place reduction, packed into the first warps
-    const int nslow = s_nslow;
-    for (int q = tid; q < nslow; q += kTileV) {
-      const int sv = v0 + s_slow[q];
-      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
-      const int scc = __ldg(p.cur + sv);
-      const int sd = (int)(sr1 - sr0);
-      int sbest;
-      if (UNIT) {
-        sbest = slow_vertex_unit<MULTI>(p, s_comm, s_cnt, (int)(sr0 - E0), sd, sv, scc, acc_le_u);
-        if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
-      } else {
-        double svdeg;
-        sbest = slow_vertex_w<MULTI>(p, s_comm, s_w, (int)(sr0 - E0), sd, sv, scc, acc_le_d, svdeg);
-        if (sbest != scc) push_move_w<MULTI>(p, scc, sbest, svdeg);
-      }
-      p.tgt[sv] = sbest;
-      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
-    }
-    start = end;
-    __syncthreads();
-  }
-
-  const int lane = tid & 31, wid = tid >> 5;
-  if (UNIT) { const unsigned long long s = warp_sum(acc_le_u); if (lane == 0) s_red[0][wid] = s; }
-  else { const double s = warp_sum(acc_le_d); if (lane == 0) s_redd[wid] = s; }
-  if (TRACE) {
-    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
-    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (UNIT) {
-      unsigned long long s = 0;
-      for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
-      if (s) atomicAdd(&p.acc->le_u, s);
-    } else {
-      double s = 0;
-      for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
-      if (s != 0.0) atomicAdd(&p.acc->le_d, s);
-    }
-    if (TRACE) {
-      unsigned long long a = 0, b = 0;
-      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
-      atomicAdd(&p.acc->moved, a);
-      atomicAdd(&p.acc->hash, b);
-    }
-  }
+  atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
+  atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
+  atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, co) + ci), ~0ULL);
+  atomicAdd(ptr_udeg<MULTI>(p, co) + ci, -vdeg);
 }
 
 // ----------------------------------------------------------------------------------------------
-// Scan kernel, fourth generation ("warp-synchronous loops").  Same tiles and phase A as k_scan.  Profiling k_scan
+// Scan kernel, second generation ("warp-synchronous loops"), the default.  Same tiles and phase A as k_scan.  Profiling k_scan
 // once the layout had locality showed it issue-bound at 12 of 32 lanes active: in the in-place reduction every
 // lane starts its inner "count this community" loop at a different moment, so the warp serialises them.  Here
 // phase B is arranged so that the lanes of a warp run the same loop at the same time:
@@ -956,11 +582,11 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     if (d) {
       locate<MULTI>(p.pt, p.base, cc, owner, idx);
       if (UNIT) {
-        cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+        cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
         vdeg = (double)d;
         sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
       } else {
-        cc_deg = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->degree);
+        cc_deg = __ldg(&(ptr_cinfo_w<MULTI>(p, owner) + idx)->degree);
         vdeg = __ldg(p.vdeg + v);
         sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
       }
@@ -987,8 +613,8 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
       if (has) {
         ck = s_comm[o0 + k];
         locate<MULTI>(p.pt, p.base, ck, yo, yi);
-        if (UNIT) ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
-        else ay = __ldg(&((MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0]) + yi)->degree);
+        if (UNIT) ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
+        else ay = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
         sum = UNIT ? 1.0 : s_w[o0 + k];
       }
       int c = 1;
@@ -1011,11 +637,11 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
         locate<MULTI>(p.pt, p.base, best, bo, bi);
         long long sz_cc, sz_b;
         if (UNIT) {
-          sz_cc = __ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
-          sz_b = __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi);
+          sz_cc = __ldg(ptr_csize<MULTI>(p, owner) + idx);
+          sz_b = __ldg(ptr_csize<MULTI>(p, bo) + bi);
         } else {
-          sz_cc = __ldg(&((MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0]) + idx)->size);
-          sz_b = __ldg(&((MULTI ? p.pt.cinfo_w[bo] : p.pt.cinfo_w[0]) + bi)->size);
+          sz_cc = __ldg(&(ptr_cinfo_w<MULTI>(p, owner) + idx)->size);
+          sz_b = __ldg(&(ptr_cinfo_w<MULTI>(p, bo) + bi)->size);
         }
         if (sz_cc == 1 && sz_b == 1) best = cc;
       }
@@ -1048,165 +674,6 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
       for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
       if (s != 0.0) atomicAdd(&p.acc->le_d, s);
     }
-    if (TRACE) {
-      unsigned long long a = 0, b = 0;
-      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
-      atomicAdd(&p.acc->moved, a);
-      atomicAdd(&p.acc->hash, b);
-    }
-  }
-}
-
-// ----------------------------------------------------------------------------------------------
-// Unit-weight scan kernel, fifth generation ("private hash tables").  k_scan_ws is still issue-bound: its outer
-// loop runs max-over-lanes(distinct communities) rounds and every round walks the rest of the segment.  Here each
-// thread owns a kHtSlots-entry open-addressing table in shared memory (column-major: slot h of thread t lives at
-// [h][t], so a warp never has bank conflicts whatever slots its lanes probe) and makes ONE pass over its staged
-// neighbours: O(d) probes instead of O(rounds x d) compares.  A bit mask of occupied slots drives the gain loop.
-// Vertices with more distinct neighbour communities than slots are queued and handled by the in-place reduction.
-// ----------------------------------------------------------------------------------------------
-constexpr int kHtSlots = 16;
-
-template <bool MULTI, bool TRACE>
-__global__ void __launch_bounds__(kTileV) k_scan_ht(const ScanParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);                 // kECap staged communities
-  int32_t *s_key = s_comm + kECap;                                         // [kHtSlots][kTileV]
-  int32_t *s_val = s_key + kHtSlots * kTileV;                              // [kHtSlots][kTileV]; doubles as s_cnt for the slow path
-  __shared__ int s_next, s_nslow, s_end, s_skip;
-  __shared__ uint32_t s_e0;
-  __shared__ int s_slow[kTileV];
-  __shared__ unsigned long long s_red[3][kTileV / 32];
-
-  const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * kTileV;
-  const int v1 = min(p.lnv, v0 + kTileV);
-  const int v = v0 + tid;
-  const unsigned long long pol_str = make_policy((p.cache_policy & 4) ? 2 : 0);
-  uint32_t r0 = 0, r1 = 0;
-  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
-  const uint32_t deg = r1 - r0;
-  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
-  unsigned long long acc_le = 0, acc_moved = 0, acc_hash = 0;
-
-  int start = v0;
-  while (start < v1) {
-    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; s_nslow = 0; }
-#pragma unroll
-    for (int h = 0; h < kHtSlots; h++) s_key[h * kTileV + tid] = -1;       // clear my table
-    __syncthreads();
-    if (s_skip) { start++; __syncthreads(); continue; }
-    const uint32_t E0 = s_e0;
-    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
-    __syncthreads();
-    const int end = s_end;
-    if (tid == end - 1 - v0) s_next = (int)r1;
-    __syncthreads();
-    const int ne = (int)((uint32_t)s_next - E0);
-
-    // ---- phase A
-    {
-      const int32_t *tl = p.tails + E0;
-      int i = tid;
-      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
-        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
-                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
-        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
-        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
-      }
-      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
-    }
-    __syncthreads();
-
-    // ---- phase B: one pass, private hash table
-    const bool mine = (v >= start && v < end);
-    const int d = mine ? (int)deg : 0;
-    const int o0 = mine ? (int)(r0 - E0) : 0;
-    int cc = 0, best = 0;
-    if (mine) { cc = __ldg(p.cur + v); best = cc; }
-    int owner = 0; long long idx = 0;
-    double cc_deg = 0.0;
-    if (d) {
-      locate<MULTI>(p.pt, p.base, cc, owner, idx);
-      cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
-    }
-    int cnt0 = 0, nd = 0;
-    unsigned int occ = 0;
-    bool overflow = false;
-    int32_t *my_key = s_key + tid, *my_val = s_val + tid;
-    for (int k = 0; k < d; k++) {
-      const int c = s_comm[o0 + k];
-      if (c == cc) { cnt0++; continue; }
-      unsigned int h = ((unsigned int)c * 0x9E3779B1u) >> (32 - 4);
-      bool placed = false;
-#pragma unroll 1
-      for (int probe = 0; probe < kHtSlots; probe++) {
-        const int key = my_key[h * kTileV];
-        if (key == c) { my_val[h * kTileV]++; placed = true; break; }
-        if (key == -1) { my_key[h * kTileV] = c; my_val[h * kTileV] = 1; occ |= 1u << h; nd++; placed = true; break; }
-        h = (h + 1) & (kHtSlots - 1);
-      }
-      if (!placed) { overflow = true; break; }
-    }
-    bool done = mine;
-    if (overflow) { done = false; s_slow[atomicAdd(&s_nslow, 1)] = tid; }
-    else if (d) {
-      const double vdeg = (double)d;
-      const double sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
-      const double eix = __dsub_rn((double)cnt0, sl), ax = __dsub_rn(cc_deg, vdeg);
-      acc_le += (unsigned long long)cnt0;
-      double bg = 0.0;
-      int lbest = kNoLabel;
-      while (occ) {
-        const int h = __ffs(occ) - 1;
-        occ &= occ - 1;
-        const int y = my_key[h * kTileV];
-        int yo; long long yi;
-        locate<MULTI>(p.pt, p.base, y, yo, yi);
-        const double ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi);
-        const double g = gain_of((double)my_val[h * kTileV], eix, vdeg, ay, ax, p.constant);
-        if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
-      }
-      if (label_greater<MULTI>(p, best, lbest, cc)) {                        // singleton veto, dspl.hpp:224-225
-        int bo; long long bi;
-        locate<MULTI>(p.pt, p.base, best, bo, bi);
-        if (__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx) == 1 && __ldg((MULTI ? p.pt.csize[bo] : p.pt.csize[0]) + bi) == 1)
-          best = cc;
-      }
-      if (best != cc) push_move_unit<MULTI>(p, cc, best, d);                 // dspl.hpp:331-399
-    }
-    if (done) {
-      st_pol(p.tgt + v, best, pol_str);                                      // dspl.hpp:404
-      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
-    }
-    __syncthreads();
-    // ---- overflowed vertices: in-place reduction (uses s_val as the count array), packed into the first warps
-    const int nslow = s_nslow;
-    for (int q = tid; q < nslow; q += kTileV) {
-      const int sv = v0 + s_slow[q];
-      const uint32_t sr0 = p.rowptr[sv], sr1 = p.rowptr[sv + 1];
-      const int scc = __ldg(p.cur + sv);
-      const int sd = (int)(sr1 - sr0);
-      const int sbest = slow_vertex_unit<MULTI>(p, s_comm, s_val, (int)(sr0 - E0), sd, sv, scc, acc_le);
-      if (sbest != scc) push_move_unit<MULTI>(p, scc, sbest, sd);
-      p.tgt[sv] = sbest;
-      if (TRACE) { acc_moved += (sbest != scc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + sv)), label_of<MULTI>(p, sbest)); }
-    }
-    start = end;
-    __syncthreads();
-  }
-
-  const int lane = tid & 31, wid = tid >> 5;
-  { const unsigned long long s = warp_sum(acc_le); if (lane == 0) s_red[0][wid] = s; }
-  if (TRACE) {
-    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
-    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long s = 0;
-    for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
-    if (s) atomicAdd(&p.acc->le_u, s);
     if (TRACE) {
       unsigned long long a = 0, b = 0;
       for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
@@ -1261,12 +728,12 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
   locate<MULTI>(p.pt, p.base, cc, owner, idx);
   double cc_deg, vdeg, sl; long long cc_size;
   if (UNIT) {
-    cc_size = (long long)__ldg((MULTI ? p.pt.csize[owner] : p.pt.csize[0]) + idx);
-    cc_deg = (double)__ldg((MULTI ? p.pt.cdeg[owner] : p.pt.cdeg[0]) + idx);
+    cc_size = (long long)__ldg(ptr_csize<MULTI>(p, owner) + idx);
+    cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
     vdeg = (double)(e1 - e0);
     sl = p.has_self ? (double)p.self_i[v] : 0.0;
   } else {
-    const CommW cw = (MULTI ? p.pt.cinfo_w[owner] : p.pt.cinfo_w[0])[idx];
+    const CommW cw = ptr_cinfo_w<MULTI>(p, owner)[idx];
     cc_size = cw.size; cc_deg = cw.degree;
     vdeg = p.vdeg[v];
     sl = p.has_self ? p.self_d[v] : 0.0;
@@ -1282,10 +749,10 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     locate<MULTI>(p.pt, p.base, y, yo, yi);
     double ay, eiy; long long ysz;
     if (UNIT) {
-      ysz = (long long)__ldg((MULTI ? p.pt.csize[yo] : p.pt.csize[0]) + yi);
-      ay = (double)__ldg((MULTI ? p.pt.cdeg[yo] : p.pt.cdeg[0]) + yi); eiy = (double)vi[i];
+      ysz = (long long)__ldg(ptr_csize<MULTI>(p, yo) + yi);
+      ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi); eiy = (double)vi[i];
     } else {
-      const CommW cw = (MULTI ? p.pt.cinfo_w[yo] : p.pt.cinfo_w[0])[yi];
+      const CommW cw = ptr_cinfo_w<MULTI>(p, yo)[yi];
       ysz = cw.size; ay = cw.degree; eiy = vd[i];
     }
     const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
@@ -1316,13 +783,13 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
       int bo; long long bi;
       locate<MULTI>(p.pt, p.base, best, bo, bi);
       if (UNIT) {
-        atomicAdd((MULTI ? p.pt.upd[bo] : p.pt.upd[0]) + bi, pack_delta(1, (long long)(e1 - e0)));
-        atomicAdd((MULTI ? p.pt.upd[owner] : p.pt.upd[0]) + idx, pack_delta(-1, -(long long)(e1 - e0)));
+        atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)(e1 - e0)));
+        atomicAdd(ptr_upd<MULTI>(p, owner) + idx, pack_delta(-1, -(long long)(e1 - e0)));
       } else {
-        atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[bo] : p.pt.usize[0]) + bi), 1ULL);
-        atomicAdd((MULTI ? p.pt.udeg[bo] : p.pt.udeg[0]) + bi, vdeg);
-        atomicAdd((unsigned long long *)((MULTI ? p.pt.usize[owner] : p.pt.usize[0]) + idx), ~0ULL);
-        atomicAdd((MULTI ? p.pt.udeg[owner] : p.pt.udeg[0]) + idx, -vdeg);
+        atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
+        atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
+        atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, owner) + idx), ~0ULL);
+        atomicAdd(ptr_udeg<MULTI>(p, owner) + idx, -vdeg);
       }
     }
     p.tgt[v] = best;

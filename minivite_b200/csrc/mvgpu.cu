@@ -134,8 +134,9 @@ struct mvgpu_ctx {
   int32_t *peer_comm[2][kMaxRanks];
   PeerTable pt;
   std::vector<void *> ipc_opened;
-  bool peers_ready = false;
+  bool peers_ready = false, ipc_valid = false;
   int peers_unit = -1;
+  void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
   int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
@@ -214,15 +215,27 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     pt.cdeg[0] = c->cdeg.p; pt.csize[0] = c->csize.p; pt.upd[0] = c->upd.p; pt.cinfo_w[0] = c->cinfo_w.p; pt.usize[0] = c->usize.p; pt.udeg[0] = c->udeg.p;
     return 0;
   }
-  if (c->peers_ready && c->peers_unit == unit * 2 + c->relabel) return 0;
+  void *ptrs[10] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
+                    unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
+                    unit ? nullptr : (void *)c->udeg.p, c->relabel ? (void *)c->lab.p : nullptr,
+                    (void *)c->comm_a.p, (void *)c->comm_b.p, (void *)c->p2p.p};
+  if (c->peers_ready) return 0;            // same graph, same buffers: tables are still valid
+  // IPC handles are expensive to (re)open: skip the exchange when no rank's buffers moved since the last one
+  long long changed = c->ipc_valid ? 0 : 1;
+  for (int k = 0; k < 10; k++) if (ptrs[k] != c->last_ptrs[k]) changed = 1;
+  {
+    Scalars *d_sc = reinterpret_cast<Scalars *>(c->scratch.p);
+    CK(cudaMemcpyAsync(d_sc->counts, &changed, sizeof changed, cudaMemcpyHostToDevice, c->stream));
+    NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclMax, c->comm, c->stream));
+    CK(cudaMemcpyAsync(&changed, d_sc->counts, sizeof changed, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if (changed) {
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
+  c->ipc_valid = false;
   PeerBlob mine;
   memset(&mine, 0, sizeof mine);
-  void *ptrs[10] = {unit ? (void *)c->cdeg.p : nullptr, unit ? (void *)c->csize.p : nullptr, unit ? (void *)c->upd.p : nullptr,
-                   unit ? nullptr : (void *)c->cinfo_w.p, unit ? nullptr : (void *)c->usize.p,
-                   unit ? nullptr : (void *)c->udeg.p, c->relabel ? (void *)c->lab.p : nullptr,
-                   (void *)c->comm_a.p, (void *)c->comm_b.p, (void *)c->p2p.p};
   for (int k = 0; k < 10; k++) {
     mine.raw[k] = (unsigned long long)ptrs[k];
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
@@ -261,6 +274,9 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     c->peer_comm[0][r] = (int32_t *)q[7]; c->peer_comm[1][r] = (int32_t *)q[8];
     c->pp.st[r] = (P2PState *)q[9];
   }
+  for (int k = 0; k < 10; k++) c->last_ptrs[k] = ptrs[k];
+  c->ipc_valid = true;
+  }
   // where my send segments land in each peer's community array: its lnv + its receive offset for me
   {
     DevBuf<long long> d_gb;
@@ -292,21 +308,13 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
   static bool attr_done = false;
   if (!attr_done) {
     CK(cudaFuncSetAttribute(k_scan<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (UNIT) CK(cudaFuncSetAttribute(k_scan_fast<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_scan_rc<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_scan_ws<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (UNIT) CK(cudaFuncSetAttribute(k_scan_ht<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(int32_t) * (kECap + 2 * kHtSlots * kTileV))));
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
   if (tiles > 0) {
-    if (UNIT && c->opt_scan_variant == 1) k_scan_fast<MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
-    else if (c->opt_scan_variant == 2) k_scan_rc<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
-    else if (c->opt_scan_variant == 4 && UNIT)
-      k_scan_ht<MULTI, TRACE><<<tiles, kTileV, sizeof(int32_t) * (kECap + 2 * kHtSlots * kTileV), c->stream>>>(sp);
-    else if (c->opt_scan_variant == 3 || c->opt_scan_variant == 4) k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
-    else k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    if (c->opt_scan_variant == 0) k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
+    else k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   }
   if (c->nheavy > 0) {
@@ -640,6 +648,8 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
   sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
   sp.pt = c->pt;
+  sp.loc_cdeg = c->cdeg.p; sp.loc_csize = c->csize.p; sp.loc_upd = c->upd.p; sp.loc_cinfo_w = c->cinfo_w.p;
+  sp.loc_usize = c->usize.p; sp.loc_udeg = c->udeg.p; sp.loc_lab = c->relabel ? c->lab.p : nullptr;
   c->last_sp = sp;
 
   struct HostMail { Acc acc; double red2[2]; unsigned long long tr2[2]; unsigned int p2p_error; };
@@ -908,6 +918,7 @@ int mvgpu_get_communities(mvgpu_ctx *c, int64_t *out) {
 int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   if (!c || !name) return fail("null argument");
   const std::string n(name);
+  c->peers_ready = false;          // options may change which arrays exist: re-validate the peer tables
   if (n == "trace") c->opt_trace = value != 0;
   else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
   else if (n == "force_weighted") c->opt_force_weighted = value != 0;
