@@ -125,12 +125,14 @@ __device__ __forceinline__ void st_pol(int32_t *p, int v, unsigned long long pol
   asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
+struct ScanParams;
 template <bool MULTI>
-__device__ __forceinline__ void locate(const PeerTable &pt, long long base, int y, int &owner, long long &idx) {
+__device__ __forceinline__ void locate_impl(const PeerTable &pt, long long base, int lnv, int y, int &owner, long long &idx) {
   if (!MULTI) { owner = 0; idx = (long long)y - base; return; }
-  // almost every community a vertex meets is owned by its own rank: test that range first
-  const long long lo = pt.parts[pt.rank], hi = pt.parts[pt.rank + 1];
-  if ((long long)y >= lo && (long long)y < hi) { owner = pt.rank; idx = (long long)y - lo; return; }
+  // almost every community a vertex meets is owned by its own rank: test that range first (plain kernel parameters,
+  // no indexed constant-bank loads)
+  const long long i = (long long)y - base;
+  if ((unsigned long long)i < (unsigned long long)lnv) { owner = pt.rank; idx = i; return; }
   int o = 0;
 #pragma unroll 1
   while (o + 1 < pt.nranks && (long long)y >= pt.parts[o + 1]) o++;
@@ -176,7 +178,7 @@ template <bool MULTI>
 __device__ __forceinline__ int label_of(const ScanParams &p, int c) {
   if (!p.relabel) return c;
   int o; long long i;
-  locate<MULTI>(p.pt, p.base, c, o, i);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, c, o, i);
   return __ldg(ptr_lab<MULTI>(p, o) + i);
 }
 // better() with lazily fetched labels; lby caches the label of the current best (kNoLabel = not fetched)
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
         int nd = 0;
         // own-community Comm{size,degree}
         int owner; long long idx;
-        locate<MULTI>(p.pt, p.base, cc, owner, idx);
+        locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
         double vdeg, eix, ax, cc_deg; long long cc_size;
         if (UNIT) {
           int cnt0 = 0;
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
         for (int m = 0; m < nd; m++) {
           const int y = s_comm[o0 + m];
           int yo; long long yi;
-          locate<MULTI>(p.pt, p.base, y, yo, yi);
+          locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
           double ay, eiy; long long ysize;
           if (UNIT) {
             ysize = (long long)__ldg(ptr_csize<MULTI>(p, yo) + yi);
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
         if (best_size == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lbest, cc)) best = cc;   // dspl.hpp:224-225
         if (best != cc) {                                                    // dspl.hpp:331-399
           int bo; long long bi;
-          locate<MULTI>(p.pt, p.base, best, bo, bi);
+          locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
           if (UNIT) {
             atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
             atomicAdd(ptr_upd<MULTI>(p, owner) + idx, pack_delta(-1, -(long long)d));
@@ -409,8 +411,8 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
 template <bool MULTI>
 __device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
   int bo, co; long long bi, ci;
-  locate<MULTI>(p.pt, p.base, best, bo, bi);
-  locate<MULTI>(p.pt, p.base, cc, co, ci);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, co, ci);
   atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
   atomicAdd(ptr_upd<MULTI>(p, co) + ci, pack_delta(-1, -(long long)d));
 }
@@ -430,7 +432,7 @@ __device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_
     s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
   }
   int owner; long long idx;
-  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
   const double cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
   const double vdeg = (double)d;
   const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
@@ -441,14 +443,14 @@ __device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_
   for (int m = 0; m < nd; m++) {
     const int y = s_comm[o0 + m];
     int yo; long long yi;
-    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
     const double ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
     const double g = gain_of((double)s_cnt[o0 + m], eix, vdeg, ay, ax, p.constant);
     if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
   }
   if (label_greater<MULTI>(p, best, lbest, cc)) {                            // dspl.hpp:224-225
     int bo; long long bi;
-    locate<MULTI>(p.pt, p.base, best, bo, bi);
+    locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
     if (__ldg(ptr_csize<MULTI>(p, owner) + idx) == 1 && __ldg(ptr_csize<MULTI>(p, bo) + bi) == 1)
       best = cc;
   }
@@ -471,7 +473,7 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
     s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
   }
   int owner; long long idx;
-  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
   const double2 raw = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, owner) + idx));
   const long long cc_size = __double_as_longlong(raw.x);
   const double vdeg = __ldg(p.vdeg + v);
@@ -485,7 +487,7 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
   for (int m = 0; m < nd; m++) {
     const int y = s_comm[o0 + m];
     int yo; long long yi;
-    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
     const double2 ry = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, yo) + yi));
     const double g = gain_of(s_w[o0 + m], eix, vdeg, ry.y, ax, p.constant);
     if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; best_size = __double_as_longlong(ry.x); }
@@ -497,8 +499,8 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
 template <bool MULTI>
 __device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int best, double vdeg) {
   int bo, co; long long bi, ci;
-  locate<MULTI>(p.pt, p.base, best, bo, bi);
-  locate<MULTI>(p.pt, p.base, cc, co, ci);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, co, ci);
   atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
   atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
   atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, co) + ci), ~0ULL);
@@ -510,10 +512,12 @@ __device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int bes
 // once the layout had locality showed it issue-bound at 12 of 32 lanes active: in the in-place reduction every
 // lane starts its inner "count this community" loop at a different moment, so the warp serialises them.  Here
 // phase B is arranged so that the lanes of a warp run the same loop at the same time:
-//   pass 0   counter[0] = weight towards the own community (one uniform walk over the staged segment);
-//   pass 1   repeat { every lane skips to its next not-yet-counted neighbour community; all lanes count their
-//            community together (one walk over the rest of the segment, marking duplicates); the community degree
-//            gather issued before the walk is consumed after it; gain + selection on registers }.
+//   pass 0   counter[0] = weight towards the own community (one uniform walk over the staged segment); the other
+//            neighbours are compacted to the front of the segment;
+//   pass 1   repeat { all lanes take the first live entry's community and count it together in one walk over their
+//            live list, compacting the rest to the front (stable: edge order survives, so weighted sums round like
+//            the reference); the community degree gather issued before the walk is consumed after it; gain +
+//            selection on registers }.
 // The trip count of the outer loop is the largest number of distinct neighbour communities among the warp's 32
 // vertices (about 4 after the first iterations) instead of the sum of all lanes' loops.  Sums are accumulated in
 // edge order per community, exactly like k_scan, so the weighted path keeps the reference's rounding.
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     int owner = 0; long long idx = 0;
     double cc_deg = 0.0, vdeg = 0.0, sl = 0.0;
     if (d) {
-      locate<MULTI>(p.pt, p.base, cc, owner, idx);
+      locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
       if (UNIT) {
         cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
         vdeg = (double)d;
@@ -591,50 +595,60 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
         sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
       }
     }
-    // pass 0: weight towards the own community, in edge order (counter[0], dspl.hpp:312-318)
+    // pass 0: weight towards the own community, in edge order (counter[0], dspl.hpp:312-318); the other
+    // neighbours are compacted to the front of the segment (stable, so edge order is kept)
     double w0 = 0.0;
-    int cnt0 = 0;
+    int cnt0 = 0, m = 0;
     for (int k = 0; k < d; k++) {
-      if (s_comm[o0 + k] == cc) { if (UNIT) cnt0++; else w0 += s_w[o0 + k]; }
+      const int x = s_comm[o0 + k];
+      if (x == cc) { if (UNIT) cnt0++; else w0 += s_w[o0 + k]; }
+      else {
+        s_comm[o0 + m] = x;
+        if (!UNIT) s_w[o0 + m] = s_w[o0 + k];
+        m++;
+      }
     }
     if (UNIT) w0 = (double)cnt0;
     const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
     if (d) { if (UNIT) acc_le_u += (unsigned long long)cnt0; else acc_le_d += w0; }
-    // pass 1: one distinct neighbour community per lane per round
+    // pass 1: one distinct neighbour community per lane per round.  The round's walk counts the community of the
+    // first live entry and compacts everything else to the front, so the live list only ever shrinks and no lane
+    // has to skip over already counted entries.
     double bg = 0.0;
     int lbest = kNoLabel;
-    int k = 0;
     for (;;) {
-      while (k < d) { const int x = s_comm[o0 + k]; if (x == cc || x < 0) k++; else break; }
-      const bool has = k < d;
+      const bool has = m > 0;
       if (!__any_sync(0xffffffffu, has)) break;
       int ck = 0, yo = 0; long long yi = 0;
-      double ay = 0.0, sum = 0.0;
+      double ay = 0.0;
       if (has) {
-        ck = s_comm[o0 + k];
-        locate<MULTI>(p.pt, p.base, ck, yo, yi);
+        ck = s_comm[o0];
+        locate_impl<MULTI>(p.pt, p.base, p.lnv, ck, yo, yi);
         if (UNIT) ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
         else ay = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
-        sum = UNIT ? 1.0 : s_w[o0 + k];
       }
-      int c = 1;
-      for (int j = k + 1; j < d; j++) {                    // d == 0 / !has lanes fall through (k >= d)
-        if (has && s_comm[o0 + j] == ck) {
-          if (UNIT) c++; else sum += s_w[o0 + j];
-          s_comm[o0 + j] = -1;
+      int c = 0, m2 = 0;
+      double sum = 0.0;
+      for (int j = 0; j < m; j++) {
+        const int x = s_comm[o0 + j];
+        if (x == ck) { if (UNIT) c++; else sum += s_w[o0 + j]; }
+        else {
+          s_comm[o0 + m2] = x;
+          if (!UNIT) s_w[o0 + m2] = s_w[o0 + j];
+          m2++;
         }
       }
+      m = m2;
       if (has) {
         if (UNIT) sum = (double)c;
         const double g = gain_of(sum, eix, vdeg, ay, ax, p.constant);
         if (better_l<MULTI>(p, g, ck, bg, best, lbest)) { bg = g; best = ck; }
-        k++;
       }
     }
     if (mine) {
       if (d && label_greater<MULTI>(p, best, lbest, cc)) {                   // singleton veto, dspl.hpp:224-225
         int bo; long long bi;
-        locate<MULTI>(p.pt, p.base, best, bo, bi);
+        locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
         long long sz_cc, sz_b;
         if (UNIT) {
           sz_cc = __ldg(ptr_csize<MULTI>(p, owner) + idx);
@@ -725,7 +739,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     if (keys[i] == cc) s_w0 = UNIT ? (double)vi[i] : vd[i];
   __syncthreads();
   int owner; long long idx;
-  locate<MULTI>(p.pt, p.base, cc, owner, idx);
+  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
   double cc_deg, vdeg, sl; long long cc_size;
   if (UNIT) {
     cc_size = (long long)__ldg(ptr_csize<MULTI>(p, owner) + idx);
@@ -746,7 +760,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     const int y = keys[i];
     if (y < 0 || y == cc) continue;
     int yo; long long yi;
-    locate<MULTI>(p.pt, p.base, y, yo, yi);
+    locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
     double ay, eiy; long long ysz;
     if (UNIT) {
       ysz = (long long)__ldg(ptr_csize<MULTI>(p, yo) + yi);
@@ -781,7 +795,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
     if (bsz == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lby, cc)) best = cc;
     if (best != cc) {
       int bo; long long bi;
-      locate<MULTI>(p.pt, p.base, best, bo, bi);
+      locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
       if (UNIT) {
         atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)(e1 - e0)));
         atomicAdd(ptr_upd<MULTI>(p, owner) + idx, pack_delta(-1, -(long long)(e1 - e0)));
