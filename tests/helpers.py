@@ -19,6 +19,16 @@ def case_graph(case):
                                          zip(ss.shards, np.cumsum([0] + [s.lne for s in ss.shards[:-1]]))])
         edges = np.concatenate([s.edges for s in ss.shards])
         return split_global(nv, rowptr.astype(np.int64), edges, p) + (ss,)
+    if kind == "file_balanced":
+        ss = hg.generate_rgg(case["n"], 1, random_edge_percent=case["pct"])
+        sh = ss.shards[0]
+        parts = np.array(case["parts"], dtype=np.int64)
+        rps, eds = [], []
+        for r in range(p):
+            a, b = parts[r], parts[r + 1]
+            rps.append(np.ascontiguousarray(sh.rowptr[a:b + 1] - sh.rowptr[a]))
+            eds.append(np.ascontiguousarray(sh.edges[sh.rowptr[a]:sh.rowptr[b]]))
+        return parts, rps, eds, ss
     if kind == "hand":
         g = case["graph"]
         edges = np.zeros(len(g["tails"]), hg.EDGE_DTYPE)

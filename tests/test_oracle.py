@@ -15,7 +15,7 @@ def _names(golden_cases, prefix):
 
 def test_golden_file_has_all_kinds(golden):
     kinds = {c["kind"] for c in golden.values()}
-    assert kinds == {"rgg", "file_rgg", "hand"}
+    assert kinds == {"rgg", "file_rgg", "hand", "file_balanced"}
     assert golden["rgg_n16384_p1"]["modularity"] == "0.75671532450841406"   # SURVEY.md 8(c) known answer
     assert golden["rgg_n16384_p1"]["final_chash"] == "5bf1e47053c42601"
 
@@ -62,3 +62,19 @@ def test_oracle_against_live_reference(tmp_path):
     res = O.louvain(ss.shards[0].parts, [s.rowptr for s in ss.shards], [s.edges for s in ss.shards])
     assert res["iters"] == ref["result"]["iters"] and res["modularity"] == ref["result"]["modularity"]
     assert [int(t["chash"]) for t in res["trace"]] == [t["chash"] for t in ref["trace"]]
+
+
+def test_balanced_reader_matches_reference_bins(golden, tmp_path):
+    """BinaryEdgeList::read_balanced (-b): same vertex bins as the reference's greedy edge balancing (graph.hpp:416-461)."""
+    from minivite_b200 import hostgraph as hg
+    case = golden["file_balanced_n16384_p4"]
+    ss = hg.generate_rgg(case["n"], 1, random_edge_percent=case["pct"])
+    path = str(tmp_path / "g.bin")
+    ss.write(path)
+    for r in range(4):
+        sh = hg.read_graph(path, r, 4, balanced=True).shards[0]
+        assert list(sh.parts) == case["parts"]
+        assert sh.base == case["parts"][r] and sh.lnv == case["parts"][r + 1] - case["parts"][r]
+    # vertex-balanced reader for comparison
+    sh = hg.read_graph(path, 1, 4, balanced=False).shards[0]
+    assert sh.base == 4096 and sh.lnv == 4096
