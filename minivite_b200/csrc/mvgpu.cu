@@ -95,7 +95,7 @@ struct mvgpu_ctx {
   DevBuf<double> weights;
   DevBuf<int32_t> self_i;
   // locality renumbering
-  DevBuf<uint32_t> bfs_key, sortkey, sortkey2, deg_new, rowptr2;
+  DevBuf<uint32_t> bfs_key, bfs_visited, sortkey, sortkey2, deg_new, rowptr2;
   DevBuf<int32_t> ids, perm, inv, lab, tails2, final_orig;
   DevBuf<double> weights2;
   DevBuf<unsigned int> level_flags;
@@ -482,7 +482,7 @@ int setup_run(mvgpu_ctx *c) {
       cudaEvent_t r0 = get_event(c, 2), r1 = get_event(c, 3);
       CK(cudaEventRecord(r0, s));
       TRY(c->perm.ensure(lnv)); TRY(c->inv.ensure(lnv)); TRY(c->lab.ensure(lnv)); TRY(c->ids.ensure(lnv));
-      TRY(c->bfs_key.ensure(lnv)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
+      TRY(c->bfs_key.ensure(lnv)); TRY(c->bfs_visited.ensure((lnv + 31) / 32 + 1)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
       TRY(c->deg_new.ensure(lnv + 1)); TRY(c->rowptr2.ensure(lnv + 1)); TRY(c->tails2.ensure(lne));
       if (!c->unit) TRY(c->weights2.ensure(lne));
       const int max_levels = 1023;
@@ -494,7 +494,8 @@ int setup_run(mvgpu_ctx *c) {
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
         const uint32_t *rp = c->rowptr.p; const int32_t *tl = c->tails.p; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
+        uint32_t *vis = c->bfs_visited.p;
+        void *args[] = {&ilnv, &rp, &tl, &key, &vis, &stride, &ml, &lf};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
         k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
         size_t tb = 0;
@@ -812,7 +813,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
   c->scratch.release(); c->cub_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
-  c->bfs_key.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
+  c->bfs_key.release(); c->bfs_visited.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
   c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
   c->weights2.release(); c->level_flags.release();
   c->p2p.release();
