@@ -25,8 +25,14 @@
 
 namespace mv {
 
-constexpr int kTileV = 256;        // vertices per CTA tile == threads per CTA
-constexpr int kECap = 4096;        // edges staged in shared memory per sub-range
+#ifndef MV_TILE_V
+#define MV_TILE_V 256
+#endif
+#ifndef MV_ECAP
+#define MV_ECAP 4096
+#endif
+constexpr int kTileV = MV_TILE_V;  // vertices per CTA tile == threads per CTA
+constexpr int kECap = MV_ECAP;     // edges staged in shared memory per sub-range
 constexpr int kMaxRanks = 16;
 
 struct Edge16 { long long tail; double weight; };          // reference graph.hpp:60-66
@@ -1008,39 +1014,25 @@ constexpr unsigned int kBfsRegionBits = 22;
 constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
-                                               uint32_t *visited, int region_stride, int max_levels, unsigned int *level_flags) {
+                                               int region_stride, int max_levels, unsigned int *level_flags) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  const int nwords = (lnv + 31) >> 5;
-  for (int i = gtid; i < nwords; i += gsz) visited[i] = 0;
   for (int v = gtid; v < lnv; v += gsz)
     key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
   grid.sync();
   const int lane = threadIdx.x & 31;
   for (int level = 0; level < max_levels; level++) {
-    // phase 1: the vertices reached in the previous level (this level's frontier) publish themselves in the 2 MB
-    // `visited` bitmap; probes of already settled neighbours then stay in L2 instead of costing a DRAM sector of key[]
     bool any = false;
-    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
-      const int v = vb + lane;
-      unsigned int k = kBfsUnreached;
-      if (v < lnv) k = __ldcg(key + v);
-      const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
-      const unsigned int m = __ballot_sync(0xffffffffu, active);
-      if (m) { any = true; if (lane == 0) visited[vb >> 5] |= m; }     // vb is a multiple of 32: this warp owns the word
-    }
-    if (__syncthreads_or(any) && threadIdx.x == 0) level_flags[level] = 1;
-    grid.sync();
-    if (__ldcg(level_flags + level) == 0) break;
-    // phase 2: every warp inspects 32 consecutive keys; the (few) frontier vertices among them are expanded by the
-    // whole warp, lanes over edges, so the probes of one vertex are in flight together
+    // every warp inspects 32 consecutive keys; the (few) frontier vertices among them are expanded by the
+    // whole warp, lanes over edges, so the random key[] probes of one vertex are in flight together
     for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
       const int v = vb + lane;
       unsigned int k = kBfsUnreached;
       if (v < lnv) k = __ldcg(key + v);
       const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
       unsigned int m = __ballot_sync(0xffffffffu, active);
+      any |= (m != 0);
       uint32_t r0 = 0, r1 = 0;
       if (active) { r0 = rowptr[v]; r1 = rowptr[v + 1]; }
       while (m) {
@@ -1051,11 +1043,13 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
         const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (kb & ((1u << kBfsRegionBits) - 1));
         for (uint32_t e = e0 + lane; e < e1; e += 32) {
           const int w = tails[e];
-          if (w < lnv && !((__ldcg(visited + (w >> 5)) >> (w & 31)) & 1u)) atomicMin(&key[w], nk);
+          if (w < lnv && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
         }
       }
     }
+    if (__syncthreads_or(any) && threadIdx.x == 0) level_flags[level] = 1;
     grid.sync();
+    if (__ldcg(level_flags + level) == 0) break;
   }
 }
 

@@ -482,7 +482,7 @@ int setup_run(mvgpu_ctx *c) {
       cudaEvent_t r0 = get_event(c, 2), r1 = get_event(c, 3);
       CK(cudaEventRecord(r0, s));
       TRY(c->perm.ensure(lnv)); TRY(c->inv.ensure(lnv)); TRY(c->lab.ensure(lnv)); TRY(c->ids.ensure(lnv));
-      TRY(c->bfs_key.ensure(lnv)); TRY(c->bfs_visited.ensure((lnv + 31) / 32 + 1)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
+      TRY(c->bfs_key.ensure(lnv)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
       TRY(c->deg_new.ensure(lnv + 1)); TRY(c->rowptr2.ensure(lnv + 1)); TRY(c->tails2.ensure(lne));
       if (!c->unit) TRY(c->weights2.ensure(lne));
       const int max_levels = 1023;
@@ -494,8 +494,7 @@ int setup_run(mvgpu_ctx *c) {
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
         const uint32_t *rp = c->rowptr.p; const int32_t *tl = c->tails.p; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        uint32_t *vis = c->bfs_visited.p;
-        void *args[] = {&ilnv, &rp, &tl, &key, &vis, &stride, &ml, &lf};
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
         k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
         size_t tb = 0;

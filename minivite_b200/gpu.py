@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvgpu.so")
+_LIB_PATH = os.environ.get("MVGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvgpu.so")
 UNIQUE_ID_BYTES = 128
 
 TRACE_DTYPE = np.dtype([("modularity", "<f8"), ("moved", "<i8"), ("chash", "<u8")])
