@@ -53,6 +53,7 @@ typedef struct {
   double reorder_s;      /* part of setup_s spent on the locality renumbering (0 when it did not run) */
   int32_t reordered;     /* 1 if this rank's vertices were renumbered for locality */
   int32_t pad_;
+  int64_t h2d_bytes;     /* bytes mvgpu_upload_shard copied host->device for the current shard (0 for attached arrays) */
 } mvgpu_timings;
 
 const char *mvgpu_last_error(void);
@@ -99,7 +100,9 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * streamed arrays; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
  * vertices per BFS region of the renumbering, default 512), "comm_mode" (multi-GPU per-iteration exchanges: 1 = stores /
- * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce). */
+ * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "compact_upload" (1 default:
+ * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 0 = always the 16-byte records),
+ * "host_threads" (OpenMP width of that host pass; 0 = OpenMP default). */
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
 int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);
 int mvgpu_get_timings(mvgpu_ctx *ctx, mvgpu_timings *out);

@@ -921,12 +921,26 @@ __global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long
   }
 }
 
+// same conversion for the compact upload format (int32 global tails, unit weights; see mvgpu_upload_shard)
+__global__ void __launch_bounds__(256) k_convert_tails32(const int32_t *gtails, long long lne, long long base, long long bound,
+                                                         int32_t *tails, long long *remote_list, unsigned long long *remote_cursor) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = __ldcs(gtails + e);
+    const bool local = (t >= base && t < bound);
+    tails[e] = local ? (int32_t)(t - base) : -1;
+    if (!local && remote_list) {
+      const unsigned long long pos = atomicAdd(remote_cursor, 1ULL);
+      remote_list[pos] = t;
+    }
+  }
+}
+
 // ghosts: slot = lnv + rank of the tail in the sorted unique ghost list
-__global__ void __launch_bounds__(256) k_remap_ghost_tails(const Edge16 *edges, long long lne, int32_t *tails,
+__global__ void __launch_bounds__(256) k_remap_ghost_tails(const Edge16 *edges, const int32_t *gtails, long long lne, int32_t *tails,
                                                            const long long *ghost_gid, int nghost, int lnv) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
     if (tails[e] >= 0) continue;
-    const long long t = edges[e].tail;
+    const long long t = edges ? edges[e].tail : (long long)gtails[e];
     int lo = 0, hi = nghost;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (ghost_gid[mid] < t) lo = mid + 1; else hi = mid; }
     tails[e] = lnv + lo;

@@ -10,6 +10,7 @@
 // removes the reference's request/reply and delta-push message rounds (dspl.hpp:719-929, 1022-1102);
 // modularity is one ncclAllReduce of two doubles (dspl.hpp:441).
 #include <cuda_runtime.h>
+#include <omp.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -88,6 +89,16 @@ struct mvgpu_ctx {
   const Edge16 *d_edges = nullptr;
   DevBuf<long long> in_rowptr;
   DevBuf<Edge16> in_edges;
+  // compact upload format (unit-weight shards): int32 global tails, staged through pinned chunks
+  DevBuf<int32_t> in_tails32;
+  const int32_t *d_tails32 = nullptr;
+  long long in_nremote = 0;
+  void *h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // compact CSR the iterations run on (original numbering or renumbered)
+  const uint32_t *a_rowptr = nullptr;
+  const int32_t *a_tails = nullptr;
+  const double *a_weights = nullptr;
   bool have_graph = false;
   // compact graph
   DevBuf<uint32_t> rowptr;
@@ -138,7 +149,7 @@ struct mvgpu_ctx {
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 1, opt_host_threads = 0;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -148,6 +159,7 @@ struct mvgpu_ctx {
   std::vector<double> scan_times;
   mvgpu_timings tm;
   double h2d_s = 0.0;
+  long long h2d_bytes = 0;
   // pinned host mailbox
   void *h_pin = nullptr;
   // events
@@ -346,19 +358,25 @@ int setup_run(mvgpu_ctx *c) {
   CK(cudaMemsetAsync(d_sc, 0, sizeof(Scalars), s));
   const long long lnv = c->lnv, lne = c->lne;
 
-  // pass 1 over the edges: unit weights? how many non-owned tails? (+ input validation)
-  k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
-  c->tm.kernel_launches++;
+  // pass 1 over the edges: unit weights? how many non-owned tails? (+ input validation).  The compact upload
+  // format has answered all of that on the host already.
+  const bool compact_in = c->d_tails32 != nullptr;
+  if (!compact_in) {
+    k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
+    c->tm.kernel_launches++;
+  }
   TRY(c->rowptr.ensure(lnv + 1));
   k_rowptr32<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>(c->d_rowptr64, (int)lnv, c->rowptr.p, &d_sc->maxdeg, &d_sc->bad_rowptr);
   c->tm.kernel_launches++;
   CK(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (compact_in) { h.st.nremote = (unsigned long long)c->in_nremote; h.st.nonunit = 0; h.st.bad_tail = 0; }
   if (h.st.bad_tail) return fail("edge tail outside [0, nv)");
   if (h.bad_rowptr) return fail("edge_indices not monotone");
   if (c->nranks == 1 && h.st.nremote) return fail("non-local tail in a single-rank graph");
   c->maxdeg = h.maxdeg;
   int unit = (!h.st.nonunit && !c->opt_force_weighted) ? 1 : 0;
+  if (compact_in && !unit) return fail("force_weighted needs the full edge records: set compact_upload=0");
 
   // global agreement on the path + on 2m < 2^31 needs the total weight; the weight total itself comes
   // from the vertex-init kernel below, so first settle `unit` from the flags (ne bound checked after).
@@ -376,14 +394,27 @@ int setup_run(mvgpu_ctx *c) {
   c->unit = unit != 0;
 
   // pass 2: tails -> slots, weights split off, remote tails listed
-  TRY(c->tails.ensure(lne));
-  if (!c->unit) TRY(c->weights.ensure(lne));
   const long long nremote = (long long)h.st.nremote;
   if (nremote) TRY(c->remote_list.ensure(nremote));
-  k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->tails.p,
-                                                            c->unit ? nullptr : c->weights.p,
-                                                            nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
-  c->tm.kernel_launches++;
+  const uint32_t *src_rowptr = c->rowptr.p;
+  const int32_t *src_tails = nullptr;
+  const double *src_weights = nullptr;
+  if (compact_in && c->nranks == 1) {
+    src_tails = c->d_tails32;                       // global id == local slot: the uploaded array is used as is (read-only)
+  } else {
+    TRY(c->tails.ensure(lne));
+    if (!c->unit) TRY(c->weights.ensure(lne));
+    if (compact_in)
+      k_convert_tails32<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_tails32, lne, c->base, c->bound, c->tails.p,
+                                                                  nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
+    else
+      k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->tails.p,
+                                                                c->unit ? nullptr : c->weights.p,
+                                                                nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
+    c->tm.kernel_launches++;
+    src_tails = c->tails.p;
+    src_weights = c->unit ? nullptr : c->weights.p;
+  }
 
   // ghost discovery (exchangeVertexReqs, dspl.hpp:1106-1272): sorted unique non-owned tails
   c->nghost = 0; c->nsend = 0;
@@ -411,7 +442,7 @@ int setup_run(mvgpu_ctx *c) {
       sorted.release();
       c->nghost = nu;
       if (lnv + c->nghost >= (1LL << 31)) return fail("lnv + nghost >= 2^31");
-      k_remap_ghost_tails<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
+      k_remap_ghost_tails<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(compact_in ? nullptr : c->d_edges, c->d_tails32, lne, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
       c->tm.kernel_launches++;
       // per-owner counts of my ghosts (the list is sorted, owners are contiguous ranges)
       std::vector<long long> hg(c->nghost);
@@ -461,7 +492,7 @@ int setup_run(mvgpu_ctx *c) {
     int want = c->opt_reorder == 1 ? 1 : 0;
     if (c->opt_reorder == 2 && lnv >= 65536) {
       // auto: renumber when the given numbering has no locality (mean |tail - v| above lnv/64 on a vertex sample)
-      k_span_sample<<<grid_for(lnv / 64 + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->rowptr.p, c->tails.p, 64, &d_sc->span_sum, &d_sc->span_cnt);
+      k_span_sample<<<grid_for(lnv / 64 + 1, 256, nsm), 256, 0, s>>>((int)lnv, src_rowptr, src_tails, 64, &d_sc->span_sum, &d_sc->span_cnt);
       c->tm.kernel_launches++;
       unsigned long long sp2[2];
       CK(cudaMemcpyAsync(sp2, &d_sc->span_sum, sizeof sp2, cudaMemcpyDeviceToHost, s));
@@ -493,7 +524,7 @@ int setup_run(mvgpu_ctx *c) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msbfs, 256, 0));
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
-        const uint32_t *rp = c->rowptr.p; const int32_t *tl = c->tails.p; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
+        const uint32_t *rp = src_rowptr; const int32_t *tl = src_tails; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
         void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
         k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
@@ -508,7 +539,7 @@ int setup_run(mvgpu_ctx *c) {
         k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->perm.p);
         c->tm.kernel_launches++;
       }
-      k_perm_inverse<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->perm.p, c->base, c->inv.p, c->lab.p, c->rowptr.p, c->deg_new.p);
+      k_perm_inverse<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->perm.p, c->base, c->inv.p, c->lab.p, src_rowptr, c->deg_new.p);
       c->tm.kernel_launches++;
       if (want) {
         size_t tb = 0;
@@ -516,13 +547,12 @@ int setup_run(mvgpu_ctx *c) {
         TRY(c->cub_tmp.ensure(tb));
         tb = c->cub_tmp.cap;
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, c->deg_new.p, c->rowptr2.p, (int)lnv + 1, s));
-        k_permute_adj<<<grid_for(lnv * 8, 256, nsm, 16), 256, 0, s>>>((int)lnv, c->perm.p, c->inv.p, c->rowptr.p, c->tails.p,
-                                                                    c->unit ? nullptr : c->weights.p, c->rowptr2.p, c->tails2.p,
-                                                                    c->unit ? nullptr : c->weights2.p);
+        k_permute_adj<<<grid_for(lnv * 8, 256, nsm, 16), 256, 0, s>>>((int)lnv, c->perm.p, c->inv.p, src_rowptr, src_tails, src_weights,
+                                                                    c->rowptr2.p, c->tails2.p, c->unit ? nullptr : c->weights2.p);
         c->tm.kernel_launches += 2;
-        std::swap(c->rowptr, c->rowptr2);
-        std::swap(c->tails, c->tails2);
-        if (!c->unit) std::swap(c->weights, c->weights2);
+        src_rowptr = c->rowptr2.p;
+        src_tails = c->tails2.p;
+        src_weights = c->unit ? nullptr : c->weights2.p;
         c->reordered = true;
       }
       CK(cudaEventRecord(r1, s));
@@ -534,6 +564,8 @@ int setup_run(mvgpu_ctx *c) {
     }
   }
 
+  c->a_rowptr = src_rowptr; c->a_tails = src_tails; c->a_weights = src_weights;
+
   // state arrays
   const long long nslots = lnv + c->nghost;
   TRY(c->comm_a.ensure(nslots));
@@ -544,11 +576,11 @@ int setup_run(mvgpu_ctx *c) {
   CK(cudaMemsetAsync(c->acc.p, 0, sizeof(Acc) * ((size_t)c->opt_max_iters + 2), s));
 
   if (c->unit)
-    k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, nullptr, c->comm_a.p,
+    k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, nullptr, c->comm_a.p,
                                                               c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
                                                               c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self);
   else
-    k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->rowptr.p, c->tails.p, c->weights.p, c->comm_a.p,
+    k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, c->a_weights, c->comm_a.p,
                                                                nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
                                                                nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self);
   c->tm.kernel_launches++;
@@ -561,7 +593,7 @@ int setup_run(mvgpu_ctx *c) {
   c->nheavy = 0;
   if (c->maxdeg > heavy_deg) {
     TRY(c->heavy_list.ensure(lnv));
-    k_collect_heavy<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->rowptr.p, (unsigned int)heavy_deg, c->heavy_list.p, &d_sc->heavy_count);
+    k_collect_heavy<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->a_rowptr, (unsigned int)heavy_deg, c->heavy_list.p, &d_sc->heavy_count);
     c->tm.kernel_launches++;
   }
 
@@ -581,7 +613,7 @@ int setup_run(mvgpu_ctx *c) {
     std::vector<unsigned long long> off(c->nheavy + 1, 0);
     for (long long i = 0; i < c->nheavy; i++) {
       uint32_t r2[2];
-      CK(cudaMemcpy(r2, c->rowptr.p + hl[i], sizeof r2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(r2, c->a_rowptr + hl[i], sizeof r2, cudaMemcpyDeviceToHost));
       unsigned long long T = 64;
       while (T < 2ULL * (r2[1] - r2[0])) T <<= 1;
       off[i + 1] = off[i] + T;
@@ -644,7 +676,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.base = c->base;
   sp.cache_policy = c->opt_cache_policy;
   sp.relabel = c->relabel;
-  sp.rowptr = c->rowptr.p; sp.tails = c->tails.p; sp.weights = c->unit ? nullptr : c->weights.p;
+  sp.rowptr = c->a_rowptr; sp.tails = c->a_tails; sp.weights = c->unit ? nullptr : c->a_weights;
   sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
   sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
   sp.pt = c->pt;
@@ -754,6 +786,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   }
   c->tm.iters = numIters;
   c->tm.h2d_s = c->h2d_s;
+  c->tm.h2d_bytes = c->h2d_bytes;
   *iters_out = numIters;                                       // dspl.hpp:1430
   *mod_out = prevMod;                                          // dspl.hpp:1440
   return 0;
@@ -808,6 +841,8 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+  for (int b = 0; b < 2; b++) { if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]); if (c->stage_ev[b]) cudaEventDestroy(c->stage_ev[b]); }
+  c->in_tails32.release();
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
@@ -844,24 +879,76 @@ int mvgpu_comm_init(mvgpu_ctx *c, const void *id128) {
   return 0;
 }
 
+// Host side of the compact upload: a unit-weight shard needs only its tails on the device, 4 bytes per edge
+// instead of the 16-byte {tail, weight} record.  Host threads narrow the records chunk by chunk into two pinned
+// staging buffers while the previous chunk is in flight (the copy engine and the cores overlap); validation
+// (weights all 1.0, tails in range) and the count of non-owned tails happen in the same pass.  Returns 1 when the
+// shard does not qualify (then the full records are uploaded), 0 on success, <0 on CUDA errors.
+static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const void *edge_list) {
+  const Edge16 *E = reinterpret_cast<const Edge16 *>(edge_list);
+  const long long CH = 16LL << 20;                               // edges per chunk (64 MB staged)
+  for (int b = 0; b < 2; b++) {
+    if (!c->h_stage[b]) { if (cudaMallocHost(&c->h_stage[b], CH * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); return 1; } }
+    if (!c->stage_ev[b]) { if (cudaEventCreateWithFlags(&c->stage_ev[b], cudaEventDisableTiming) != cudaSuccess) return 1; }
+  }
+  if (c->in_tails32.ensure(lne)) return -1;
+  if (c->opt_host_threads > 0) omp_set_num_threads(c->opt_host_threads);
+  const long long base = c->base, bound = c->bound;
+  long long nremote = 0;
+  int k = 0;
+  for (long long off = 0; off < lne; off += CH, k++) {
+    const long long n = std::min<long long>(CH, lne - off);
+    const int b = k & 1;
+    if (k >= 2 && cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) return -1;
+    int32_t *dst = reinterpret_cast<int32_t *>(c->h_stage[b]);
+    const Edge16 *src = E + off;
+    long long nrem = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : nrem) reduction(| : bad)
+    for (long long e = 0; e < n; e++) {
+      const long long t = src[e].tail;
+      if (src[e].weight != 1.0 || t < 0 || t >= nv_global) bad = 1;
+      dst[e] = (int32_t)t;
+      nrem += (t < base || t >= bound);
+    }
+    if (bad) { cudaStreamSynchronize(c->stream); return 1; }
+    nremote += nrem;
+    if (cudaMemcpyAsync(c->in_tails32.p + off, dst, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
+    if (cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) return -1;
+  }
+  c->in_nremote = nremote;
+  return 0;
+}
+
 int mvgpu_upload_shard(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
                        const int64_t *edge_indices, const void *edge_list) {
   if (!c || !parts || !edge_indices || (lne && !edge_list)) return fail("null argument");
   CK(cudaSetDevice(c->device));
   TRY(set_graph(c, nv_global, parts, lnv, lne));
   TRY(c->in_rowptr.ensure(lnv + 1));
-  TRY(c->in_edges.ensure(lne));
   cudaEvent_t a = get_event(c, 0), b = get_event(c, 1);
   CK(cudaEventRecord(a, c->stream));
   CK(cudaMemcpyAsync(c->in_rowptr.p, edge_indices, sizeof(long long) * (lnv + 1), cudaMemcpyHostToDevice, c->stream));
-  if (lne) CK(cudaMemcpyAsync(c->in_edges.p, edge_list, sizeof(Edge16) * lne, cudaMemcpyHostToDevice, c->stream));
+  c->d_tails32 = nullptr;
+  c->d_edges = nullptr;
+  int compact = 1;
+  if (c->opt_compact_upload && !c->opt_force_weighted && lne > 0) {
+    compact = upload_compact(c, nv_global, lne, edge_list);
+    if (compact < 0) return fail(std::string("compact upload: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  if (compact == 0) c->d_tails32 = c->in_tails32.p;
+  else {
+    TRY(c->in_edges.ensure(lne));
+    if (lne) CK(cudaMemcpyAsync(c->in_edges.p, edge_list, sizeof(Edge16) * lne, cudaMemcpyHostToDevice, c->stream));
+    c->d_edges = c->in_edges.p;
+  }
   CK(cudaEventRecord(b, c->stream));
   CK(cudaEventSynchronize(b));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, a, b));
   c->h2d_s = ms * 1e-3;
+  c->h2d_bytes = (long long)sizeof(long long) * (lnv + 1) + (compact == 0 ? (long long)sizeof(int32_t) : (long long)sizeof(Edge16)) * lne;
   c->d_rowptr64 = c->in_rowptr.p;
-  c->d_edges = c->in_edges.p;
   return 0;
 }
 
@@ -873,6 +960,8 @@ int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *pa
   TRY(set_graph(c, nv_global, parts, lnv, lne));
   c->d_rowptr64 = reinterpret_cast<const long long *>(d_edge_indices);
   c->d_edges = reinterpret_cast<const Edge16 *>(d_edge_list);
+  c->d_tails32 = nullptr;
+  c->h2d_bytes = 0;
   c->h2d_s = 0.0;
   return 0;
 }
@@ -927,6 +1016,8 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else if (n == "reorder") c->opt_reorder = (int)value;
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;
+  else if (n == "compact_upload") c->opt_compact_upload = (int)value;
+  else if (n == "host_threads") c->opt_host_threads = (int)value;
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;

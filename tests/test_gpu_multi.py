@@ -118,6 +118,8 @@ def test_multi_gpu_nccl_collectives_mode(tmp_path, golden):
     for name in ("rgg_n16384_p2", "hand_clique_ring_p2"):
         res = run_ranks(tmp_path, 2, name, comm_mode=0)
         check(res, golden[name])
+        res = run_ranks(tmp_path, 2, name, compact_upload=0)
+        check(res, golden[name])
         res = run_ranks(tmp_path, 2, name, comm_mode=0, reorder=1, region_size=64)
         check(res, golden[name])
 

@@ -228,3 +228,19 @@ def test_locality_renumbering_keeps_results(gpu, golden):
     nv, parts, rowptr, edges = as_single(case)
     res = run_single(gpu, parts, rowptr, edges, nv, reorder=1, region_size=128)
     assert abs(res["modularity"] - float(case["modularity"])) <= 1e-6
+
+
+def test_upload_formats_agree(gpu, golden):
+    """mvgpu_upload_shard narrows unit-weight shards to 4-byte tails on the host (compact_upload=1, default) or ships
+    the 16-byte records (0); weighted shards always take the full records.  Same results either way."""
+    for name in ("rgg_n65536_p1", "hand_loops_multi_p1", "file_balanced_n16384_p4"):
+        case = golden[name]
+        nv, parts, rowptr, edges = as_single(case)
+        for cu in (0, 1):
+            res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=cu, host_threads=4)
+            assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+            assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + (4 if cu else 16) * len(edges)
+    case = golden["rgg_n16384_p1_w"]
+    nv, parts, rowptr, edges = as_single(case)
+    res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=1)
+    assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + 16 * len(edges) and res["timings"]["unit_weight"] == 0
