@@ -26,13 +26,17 @@
 namespace mv {
 
 #ifndef MV_TILE_V
-#define MV_TILE_V 256
+#define MV_TILE_V 128
 #endif
 #ifndef MV_ECAP
-#define MV_ECAP 4096
+#define MV_ECAP 2048
 #endif
 constexpr int kTileV = MV_TILE_V;  // vertices per CTA tile == threads per CTA
 constexpr int kECap = MV_ECAP;     // edges staged in shared memory per sub-range
+#ifndef MV_STAGE_U
+#define MV_STAGE_U 6
+#endif
+constexpr int kStageU = MV_STAGE_U;  // phase A: independent loads in flight per thread
 constexpr int kMaxRanks = 16;
 
 struct Edge16 { long long tail; double weight; };          // reference graph.hpp:60-66
@@ -563,17 +567,25 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     __syncthreads();
     const int ne = (int)((uint32_t)s_next - E0);
 
-    // ---- phase A
+    // ---- phase A: coalesced stream of the tile's tails, gather cur[tail], stage in shared memory.  All loads of a
+    // pass are issued before the first dependent gather, and all gathers before the first store (kStageU per thread)
     {
       const int32_t *tl = p.tails + E0;
-      int i = tid;
-      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
-        const int t0 = ld_pol_stream(tl + i, pol_str), t1 = ld_pol_stream(tl + i + kTileV, pol_str),
-                  t2 = ld_pol_stream(tl + i + 2 * kTileV, pol_str), t3 = ld_pol_stream(tl + i + 3 * kTileV, pol_str);
-        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
-        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
+      for (int i0 = 0; i0 < ne; i0 += kStageU * kTileV) {
+        int t[kStageU], cm[kStageU];
+#pragma unroll
+        for (int u = 0; u < kStageU; u++) {
+          const int i = i0 + u * kTileV + tid;
+          t[u] = (i < ne) ? ld_pol_stream(tl + i, pol_str) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kStageU; u++) cm[u] = (t[u] >= 0) ? __ldg(p.cur + t[u]) : 0;
+#pragma unroll
+        for (int u = 0; u < kStageU; u++) {
+          const int i = i0 + u * kTileV + tid;
+          if (i < ne) s_comm[i] = cm[u];
+        }
       }
-      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_pol_stream(tl + i, pol_str));
       if (!UNIT) {
         const double *wl = p.weights + E0;
         for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
@@ -617,38 +629,50 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     if (UNIT) w0 = (double)cnt0;
     const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(cc_deg, vdeg);
     if (d) { if (UNIT) acc_le_u += (unsigned long long)cnt0; else acc_le_d += w0; }
-    // pass 1: one distinct neighbour community per lane per round.  The round's walk counts the community of the
-    // first live entry and compacts everything else to the front, so the live list only ever shrinks and no lane
-    // has to skip over already counted entries.
+    // pass 1: two distinct neighbour communities per lane per round.  The round's walk counts the community of the
+    // first live entry and the first community that differs from it, and compacts everything else to the front, so
+    // the live list only ever shrinks and no lane has to skip over already counted entries.
     double bg = 0.0;
     int lbest = kNoLabel;
     for (;;) {
       const bool has = m > 0;
       if (!__any_sync(0xffffffffu, has)) break;
-      int ck = 0, yo = 0; long long yi = 0;
-      double ay = 0.0;
+      int ck1 = 0, yo = 0; long long yi = 0;
+      double ay1 = 0.0;
       if (has) {
-        ck = s_comm[o0];
-        locate_impl<MULTI>(p.pt, p.base, p.lnv, ck, yo, yi);
-        if (UNIT) ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
-        else ay = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
+        ck1 = s_comm[o0];
+        locate_impl<MULTI>(p.pt, p.base, p.lnv, ck1, yo, yi);
+        if (UNIT) ay1 = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
+        else ay1 = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
       }
-      int c = 0, m2 = 0;
-      double sum = 0.0;
+      int ck2 = -1, c1 = 0, c2 = 0, m2 = 0;
+      double sum1 = 0.0, sum2 = 0.0;
       for (int j = 0; j < m; j++) {
         const int x = s_comm[o0 + j];
-        if (x == ck) { if (UNIT) c++; else sum += s_w[o0 + j]; }
+        if (x == ck1) { if (UNIT) c1++; else sum1 += s_w[o0 + j]; }
         else {
-          s_comm[o0 + m2] = x;
-          if (!UNIT) s_w[o0 + m2] = s_w[o0 + j];
-          m2++;
+          if (ck2 < 0) ck2 = x;
+          if (x == ck2) { if (UNIT) c2++; else sum2 += s_w[o0 + j]; }
+          else {
+            s_comm[o0 + m2] = x;
+            if (!UNIT) s_w[o0 + m2] = s_w[o0 + j];
+            m2++;
+          }
         }
       }
       m = m2;
       if (has) {
-        if (UNIT) sum = (double)c;
-        const double g = gain_of(sum, eix, vdeg, ay, ax, p.constant);
-        if (better_l<MULTI>(p, g, ck, bg, best, lbest)) { bg = g; best = ck; }
+        if (UNIT) sum1 = (double)c1;
+        const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant);
+        if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
+        if (ck2 >= 0) {
+          locate_impl<MULTI>(p.pt, p.base, p.lnv, ck2, yo, yi);
+          double ay2;
+          if (UNIT) { ay2 = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi); sum2 = (double)c2; }
+          else ay2 = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
+          const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant);
+          if (better_l<MULTI>(p, g2, ck2, bg, best, lbest)) { bg = g2; best = ck2; }
+        }
       }
     }
     if (mine) {
