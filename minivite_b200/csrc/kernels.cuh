@@ -928,21 +928,44 @@ __global__ void __launch_bounds__(256) k_edge_stats(const Edge16 *edges, long lo
   }
 }
 
-// tails -> local slot (ghosts provisionally -1), weights split off, remote tails appended to a list
+// tails -> local slot (ghosts provisionally -1), weights split off, remote tails appended to a list.  With `st`
+// the pass also gathers the statistics of k_edge_stats (single-rank runs need no separate statistics pass).
 __global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long long lne, long long base, long long bound,
-                                                       int32_t *tails, double *weights, long long *remote_list,
-                                                       unsigned long long *remote_cursor) {
+                                                       long long nv_global, int32_t *tails, double *weights,
+                                                       long long *remote_list, unsigned long long *remote_cursor, EdgeStats *st) {
+  unsigned long long nrem = 0;
+  unsigned int nonunit = 0, bad = 0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
     const double2 raw = __ldcs(reinterpret_cast<const double2 *>(edges + e));
     const long long t = __double_as_longlong(raw.x);
     const bool local = (t >= base && t < bound);
     tails[e] = local ? (int32_t)(t - base) : -1;
     if (weights) weights[e] = raw.y;
+    if (st) {
+      if (raw.y != 1.0) nonunit = 1;
+      if (t < 0 || t >= nv_global) bad = 1;
+      else if (!local) nrem++;
+    }
     if (!local && remote_list) {
       const unsigned long long pos = atomicAdd(remote_cursor, 1ULL);
       remote_list[pos] = t;
     }
   }
+  if (st) {
+    nrem = warp_sum(nrem);
+    nonunit = __any_sync(0xffffffffu, nonunit);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (nrem) atomicAdd(&st->nremote, nrem);
+      if (nonunit) atomicOr(&st->nonunit, 1u);
+      if (bad) atomicOr(&st->bad_tail, 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_extract_weights(const Edge16 *edges, long long lne, double *weights) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x)
+    weights[e] = __ldcs(&edges[e].weight);
 }
 
 // same conversion for the compact upload format (int32 global tails, unit weights; see mvgpu_upload_shard)

@@ -361,7 +361,13 @@ int setup_run(mvgpu_ctx *c) {
   // pass 1 over the edges: unit weights? how many non-owned tails? (+ input validation).  The compact upload
   // format has answered all of that on the host already.
   const bool compact_in = c->d_tails32 != nullptr;
-  if (!compact_in) {
+  const bool fused_stats = !compact_in && c->nranks == 1;      // single rank: statistics ride on the conversion pass
+  if (fused_stats) {
+    TRY(c->tails.ensure(lne));
+    k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, c->tails.p,
+                                                              nullptr, nullptr, nullptr, &d_sc->st);
+    c->tm.kernel_launches++;
+  } else if (!compact_in) {
     k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
     c->tm.kernel_launches++;
   }
@@ -401,6 +407,14 @@ int setup_run(mvgpu_ctx *c) {
   const double *src_weights = nullptr;
   if (compact_in && c->nranks == 1) {
     src_tails = c->d_tails32;                       // global id == local slot: the uploaded array is used as is (read-only)
+  } else if (fused_stats) {
+    src_tails = c->tails.p;                         // converted by the fused pass above
+    if (!c->unit) {
+      TRY(c->weights.ensure(lne));
+      k_extract_weights<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->weights.p);
+      c->tm.kernel_launches++;
+      src_weights = c->weights.p;
+    }
   } else {
     TRY(c->tails.ensure(lne));
     if (!c->unit) TRY(c->weights.ensure(lne));
@@ -408,9 +422,9 @@ int setup_run(mvgpu_ctx *c) {
       k_convert_tails32<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_tails32, lne, c->base, c->bound, c->tails.p,
                                                                   nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
     else
-      k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->tails.p,
+      k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, c->tails.p,
                                                                 c->unit ? nullptr : c->weights.p,
-                                                                nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
+                                                                nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor, nullptr);
     c->tm.kernel_launches++;
     src_tails = c->tails.p;
     src_weights = c->unit ? nullptr : c->weights.p;
