@@ -298,12 +298,13 @@ def main():
 
     # ---- e2e: host arrays -> H2D -> Louvain -> assignment D2H, through the public API
     e2e_t = []
+    h_comm = torch.empty(sh.lnv, dtype=torch.int64).pin_memory().numpy()      # the user's (pinned) result buffer
     for k in range(args.warmup + args.steps):
         barrier()
         w0 = time.perf_counter()
         ctx.upload(nv_total, parts, h_rowptr.numpy(), h_edges.numpy().view(hg.EDGE_DTYPE))
         m2, it2 = ctx.louvain()
-        comm = ctx.communities()
+        comm = ctx.communities(out=h_comm)
         torch.cuda.synchronize()
         if k >= args.warmup:
             e2e_t.append(time.perf_counter() - w0)
@@ -349,7 +350,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": t_e2e * 1e3,
                     "h2d_bytes_per_step": h2d_total,
-                    "h2d_note": "unit-weight shards travel as 4-byte tails narrowed by host threads inside mvgpu_upload_shard",
+                    "path": "pinned host arrays -> mvgpu_upload_shard -> mvgpu_louvain -> mvgpu_get_communities (pinned int64 result)",
                     "d2h_bytes_per_step": int(nv_total * 8 + 16)},
             "gpu_launches": launches_total, "clocks": clocks,
             "phase_ms": {"setup": tm_last["setup_s"] * 1e3, "scan": tm_last["scan_s"] * 1e3,

@@ -91,6 +91,8 @@ struct mvgpu_ctx {
   DevBuf<Edge16> in_edges;
   // compact upload format (unit-weight shards): int32 global tails, staged through pinned chunks
   DevBuf<int32_t> in_tails32;
+  DevBuf<long long> wide;
+  void *h_bounce[2] = {nullptr, nullptr};
   const int32_t *d_tails32 = nullptr;
   long long in_nremote = 0;
   void *h_stage[2] = {nullptr, nullptr};
@@ -149,7 +151,7 @@ struct mvgpu_ctx {
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 1, opt_host_threads = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -856,7 +858,8 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   for (int b = 0; b < 2; b++) { if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]); if (c->stage_ev[b]) cudaEventDestroy(c->stage_ev[b]); }
-  c->in_tails32.release();
+  c->in_tails32.release(); c->wide.release();
+  for (int b = 0; b < 2; b++) if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
@@ -1009,12 +1012,39 @@ int mvgpu_get_communities(mvgpu_ctx *c, int64_t *out) {
   if (!c || !c->d_final) return fail("no result yet");
   if (c->lnv == 0) return 0;
   TRY(final_in_caller_order(c));
-  DevBuf<long long> wide;
-  TRY(wide.ensure(c->lnv));
-  k_widen<<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>(c->final_orig.p, c->lnv, wide.p);
-  CK(cudaMemcpyAsync(out, wide.p, sizeof(long long) * c->lnv, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  wide.release();
+  TRY(c->wide.ensure(c->lnv));
+  k_widen<<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>(c->final_orig.p, c->lnv, c->wide.p);
+  // pageable destinations are copied through a pinned bounce buffer in chunks (full PCIe rate instead of the
+  // driver's staged pageable path); a pinned destination is detected and written directly
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned) {
+    CK(cudaMemcpyAsync(out, c->wide.p, sizeof(long long) * c->lnv, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  const long long CH = 4LL << 20;                                  // 4 Mi entries = 32 MB per bounce buffer
+  for (int b = 0; b < 2; b++)
+    if (!c->h_bounce[b]) CK(cudaMallocHost(&c->h_bounce[b], CH * sizeof(long long)));
+  struct { long long off, n; } pend[2] = {{0, 0}, {0, 0}};
+  cudaEvent_t ev[2] = {get_event(c, 0), get_event(c, 1)};
+  long long off = 0;
+  for (int k = 0; off < c->lnv || pend[0].n || pend[1].n; k++) {
+    const int b = k & 1;
+    if (pend[b].n) {                                               // drain this buffer (its DMA was issued two steps ago,
+      CK(cudaEventSynchronize(ev[b]));                             //  the other buffer's DMA is in flight meanwhile)
+      memcpy(out + pend[b].off, c->h_bounce[b], sizeof(long long) * pend[b].n);
+      pend[b].n = 0;
+    }
+    if (off < c->lnv) {
+      const long long n = std::min<long long>(CH, c->lnv - off);
+      CK(cudaMemcpyAsync(c->h_bounce[b], c->wide.p + off, sizeof(long long) * n, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaEventRecord(ev[b], c->stream));
+      pend[b].off = off; pend[b].n = n;
+      off += n;
+    }
+  }
   return 0;
 }
 

@@ -130,10 +130,14 @@ class LouvainGPU:
         _ck(lib().mvgpu_louvain(self._h, lower, thresh, ctypes.byref(iters), ctypes.byref(mod)))
         return mod.value, iters.value
 
-    def communities(self):
-        out = np.zeros(self.lnv, dtype=np.int64)
+    def communities(self, out=None):
+        """currComm of this rank's vertices (global community ids).  `out`: optional preallocated int64 array
+        (a pinned one is filled at full PCIe rate)."""
+        if out is None:
+            out = np.empty(self.lnv, dtype=np.int64)
+        assert out.dtype == np.int64 and out.size >= self.lnv and out.flags["C_CONTIGUOUS"]
         _ck(lib().mvgpu_get_communities(self._h, out.ctypes.data))
-        return out
+        return out[:self.lnv]
 
     def trace(self):
         n = ctypes.c_int(0)
