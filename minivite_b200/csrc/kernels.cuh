@@ -176,11 +176,7 @@ __device__ __forceinline__ double gain_of(double eiy, double eix, double vdeg, d
   return __dsub_rn(t1, t2);
 }
 
-// (gain, id) ordering of dspl.hpp:214-215: larger gain wins; equal non-zero gains -> smaller id.
-__device__ __forceinline__ bool better(double g, int y, double bg, int by) {
-  return (g > bg) || ((g == bg) && (g != 0.0) && (y < by));
-}
-
+// (gain, id) ordering of dspl.hpp:214-215: larger gain wins; equal non-zero gains -> smaller id (better_l below).
 // Locality renumbering keeps the reference's semantics by comparing LABELS (original global vertex ids of
 // the community founders) wherever the reference compares community ids (dspl.hpp:215, 224).
 constexpr int kNoLabel = (int)0x80000000;
@@ -1288,9 +1284,6 @@ __global__ void __launch_bounds__(256) k_gid_to_lid(const long long *gid, int n,
 }
 __global__ void __launch_bounds__(256) k_apply_inv(int32_t *lid, int n, const int32_t *inv) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) lid[i] = inv[lid[i]];
-}
-__global__ void __launch_bounds__(256) k_init_ghost_comm(const long long *ghost_gid, int n, int32_t *comm_ghost) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) comm_ghost[i] = (int32_t)ghost_gid[i];
 }
 
 }  // namespace mv

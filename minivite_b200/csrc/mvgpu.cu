@@ -622,7 +622,6 @@ int setup_run(mvgpu_ctx *c) {
   if (c->maxdeg > heavy_deg) {
     c->nheavy = h.heavy_count;
     std::vector<int32_t> hl(c->nheavy);
-    std::vector<uint32_t> rp;   // degrees of the heavy vertices
     CK(cudaMemcpy(hl.data(), c->heavy_list.p, sizeof(int32_t) * c->nheavy, cudaMemcpyDeviceToHost));
     std::sort(hl.begin(), hl.end());
     CK(cudaMemcpy(c->heavy_list.p, hl.data(), sizeof(int32_t) * c->nheavy, cudaMemcpyHostToDevice));
