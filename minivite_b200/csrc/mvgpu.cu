@@ -10,15 +10,16 @@
 // removes the reference's request/reply and delta-push message rounds (dspl.hpp:719-929, 1022-1102);
 // modularity is one ncclAllReduce of two doubles (dspl.hpp:441).
 #include <cuda_runtime.h>
-#include <omp.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <cub/cub.cuh>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mvgpu.h"
@@ -95,8 +96,8 @@ struct mvgpu_ctx {
   void *h_bounce[2] = {nullptr, nullptr};
   const int32_t *d_tails32 = nullptr;
   long long in_nremote = 0;
-  void *h_stage[2] = {nullptr, nullptr};
-  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  void *h_stage = nullptr;
+  size_t h_stage_cap = 0;
   // compact CSR the iterations run on (original numbering or renumbered)
   const uint32_t *a_rowptr = nullptr;
   const int32_t *a_tails = nullptr;
@@ -856,7 +857,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
-  for (int b = 0; b < 2; b++) { if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]); if (c->stage_ev[b]) cudaEventDestroy(c->stage_ev[b]); }
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   c->in_tails32.release(); c->wide.release();
   for (int b = 0; b < 2; b++) if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
@@ -895,44 +896,67 @@ int mvgpu_comm_init(mvgpu_ctx *c, const void *id128) {
   return 0;
 }
 
-// Host side of the compact upload: a unit-weight shard needs only its tails on the device, 4 bytes per edge
-// instead of the 16-byte {tail, weight} record.  Host threads narrow the records chunk by chunk into two pinned
-// staging buffers while the previous chunk is in flight (the copy engine and the cores overlap); validation
-// (weights all 1.0, tails in range) and the count of non-owned tails happen in the same pass.  Returns 1 when the
-// shard does not qualify (then the full records are uploaded), 0 on success, <0 on CUDA errors.
+// Host side of the compact upload (opt-in): a unit-weight shard needs only its tails on the device, 4 bytes per
+// edge instead of the 16-byte {tail, weight} record.  A handful of plain std::threads (they block, they never spin:
+// OpenMP workers that keep spinning after a parallel region slow the CUDA submission thread down) narrow the
+// records chunk by chunk into one pinned staging array while the calling thread ships every finished chunk with
+// cudaMemcpyAsync, so the copy engine and the cores overlap.  Validation (weights all 1.0, tails in range) and the
+// count of non-owned tails happen in the same pass.  Returns 1 when the shard does not qualify (then the full
+// records are uploaded), 0 on success, <0 on CUDA errors.
 static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const void *edge_list) {
   const Edge16 *E = reinterpret_cast<const Edge16 *>(edge_list);
-  const long long CH = 16LL << 20;                               // edges per chunk (64 MB staged)
-  for (int b = 0; b < 2; b++) {
-    if (!c->h_stage[b]) { if (cudaMallocHost(&c->h_stage[b], CH * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); return 1; } }
-    if (!c->stage_ev[b]) { if (cudaEventCreateWithFlags(&c->stage_ev[b], cudaEventDisableTiming) != cudaSuccess) return 1; }
+  const long long CH = 4LL << 20;                                // edges per chunk (64 MB read, 16 MB staged)
+  const long long nchunks = (lne + CH - 1) / CH;
+  if ((size_t)lne > c->h_stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->h_stage_cap = 0;
+    if (cudaMallocHost(&c->h_stage, sizeof(int32_t) * (size_t)lne) != cudaSuccess) { cudaGetLastError(); return 1; }
+    c->h_stage_cap = (size_t)lne;
   }
   if (c->in_tails32.ensure(lne)) return -1;
-  if (c->opt_host_threads > 0) omp_set_num_threads(c->opt_host_threads);
+  int32_t *stage = reinterpret_cast<int32_t *>(c->h_stage);
   const long long base = c->base, bound = c->bound;
-  long long nremote = 0;
-  int k = 0;
-  for (long long off = 0; off < lne; off += CH, k++) {
-    const long long n = std::min<long long>(CH, lne - off);
-    const int b = k & 1;
-    if (k >= 2 && cudaEventSynchronize(c->stage_ev[b]) != cudaSuccess) return -1;
-    int32_t *dst = reinterpret_cast<int32_t *>(c->h_stage[b]);
-    const Edge16 *src = E + off;
-    long long nrem = 0;
-    int bad = 0;
-#pragma omp parallel for schedule(static) reduction(+ : nrem) reduction(| : bad)
-    for (long long e = 0; e < n; e++) {
-      const long long t = src[e].tail;
-      if (src[e].weight != 1.0 || t < 0 || t >= nv_global) bad = 1;
-      dst[e] = (int32_t)t;
-      nrem += (t < base || t >= bound);
+  const int nthreads = (int)std::max<long long>(1, std::min<long long>(c->opt_host_threads > 0 ? c->opt_host_threads : 8, nchunks));
+  std::vector<std::atomic<int>> done(nchunks);
+  for (auto &d : done) d.store(0);
+  std::atomic<long long> next{0}, nremote{0};
+  std::atomic<int> bad{0};
+  auto worker = [&]() {
+    for (;;) {
+      const long long i = next.fetch_add(1);
+      if (i >= nchunks || bad.load(std::memory_order_relaxed)) break;
+      const long long off = i * CH, n = std::min<long long>(CH, lne - off);
+      const Edge16 *src = E + off;
+      int32_t *dst = stage + off;
+      long long nrem = 0;
+      int b = 0;
+      for (long long e = 0; e < n; e++) {
+        const long long t = src[e].tail;
+        b |= (src[e].weight != 1.0) | (t < 0) | (t >= nv_global);
+        dst[e] = (int32_t)t;
+        nrem += (t < base) | (t >= bound);
+      }
+      if (b) bad.store(1);
+      nremote.fetch_add(nrem);
+      done[i].store(1, std::memory_order_release);
     }
-    if (bad) { cudaStreamSynchronize(c->stream); return 1; }
-    nremote += nrem;
-    if (cudaMemcpyAsync(c->in_tails32.p + off, dst, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return -1;
-    if (cudaEventRecord(c->stage_ev[b], c->stream) != cudaSuccess) return -1;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+  int rc = 0;
+  for (long long i = 0; i < nchunks && !rc; i++) {
+    while (!done[i].load(std::memory_order_acquire)) {
+      if (bad.load(std::memory_order_relaxed)) break;
+      std::this_thread::yield();
+    }
+    if (bad.load()) break;
+    const long long off = i * CH, n = std::min<long long>(CH, lne - off);
+    if (cudaMemcpyAsync(c->in_tails32.p + off, stage + off, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = -1;
   }
-  c->in_nremote = nremote;
+  for (auto &th : pool) th.join();
+  if (rc) return rc;
+  if (bad.load()) { cudaStreamSynchronize(c->stream); return 1; }
+  c->in_nremote = nremote.load();
   return 0;
 }
 

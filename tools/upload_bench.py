@@ -20,8 +20,8 @@ h_rowptr = torch.from_numpy(np.ascontiguousarray(sh.rowptr)).pin_memory()
 h_edges = torch.from_numpy(np.ascontiguousarray(sh.edges).view(np.uint8)).pin_memory()
 rp, ed = h_rowptr.numpy(), h_edges.numpy().view(hg.EDGE_DTYPE)
 print("omp env", os.environ.get("OMP_NUM_THREADS"), "cores", len(os.sched_getaffinity(0)), flush=True)
-for spec in ["compact_upload=0", "compact_upload=1,host_threads=0", "compact_upload=1,host_threads=8", "compact_upload=1,host_threads=32",
-             "compact_upload=1,host_threads=128"]:
+for spec in ["compact_upload=0", "compact_upload=1,host_threads=4", "compact_upload=1,host_threads=8", "compact_upload=1,host_threads=16",
+             "compact_upload=1,host_threads=32", "compact_upload=1,host_threads=64"]:
     ctx = G.LouvainGPU(0, 0, 1)
     for kv in spec.split(","):
         k, v = kv.split("=")
