@@ -164,6 +164,33 @@ MV_PTR(udeg, double *)
 MV_PTR(lab, const int32_t *)
 #undef MV_PTR
 
+// element of a community array by (internal, global) community id: one 32-bit range test for the common case
+// "owned by this rank", the owner search only for remote communities
+__device__ __forceinline__ void locate_remote(const PeerTable &pt, int y, int &owner, long long &idx) {
+  int o = 0;
+#pragma unroll 1
+  while (o + 1 < pt.nranks && (long long)y >= pt.parts[o + 1]) o++;
+  owner = o;
+  idx = (long long)y - pt.parts[o];
+}
+#define MV_AT(field, type)                                                                           \
+  template <bool MULTI>                                                                              \
+  __device__ __forceinline__ type at_##field(const ScanParams &p, int y) {                           \
+    const unsigned int i = (unsigned int)(y - (int)p.base);                                          \
+    if (!MULTI || i < (unsigned int)p.lnv) return p.loc_##field + i;                                 \
+    int o; long long idx;                                                                            \
+    locate_remote(p.pt, y, o, idx);                                                                  \
+    return p.pt.field[o] + idx;                                                                      \
+  }
+MV_AT(cdeg, const uint32_t *)
+MV_AT(csize, const int32_t *)
+MV_AT(upd, unsigned long long *)
+MV_AT(cinfo_w, const CommW *)
+MV_AT(usize, long long *)
+MV_AT(udeg, double *)
+MV_AT(lab, const int32_t *)
+#undef MV_AT
+
 __device__ __forceinline__ unsigned long long pack_delta(int dsize, long long ddeg) {
   return (unsigned long long)(((long long)dsize << 32) + ddeg);
 }
@@ -183,9 +210,7 @@ constexpr int kNoLabel = (int)0x80000000;
 template <bool MULTI>
 __device__ __forceinline__ int label_of(const ScanParams &p, int c) {
   if (!p.relabel) return c;
-  int o; long long i;
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, c, o, i);
-  return __ldg(ptr_lab<MULTI>(p, o) + i);
+  return __ldg(at_lab<MULTI>(p, c));
 }
 // better() with lazily fetched labels; lby caches the label of the current best (kNoLabel = not fetched)
 template <bool MULTI>
@@ -416,11 +441,8 @@ __global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
 // ---- helpers shared by the scan kernels ----------------------------------------------------------------
 template <bool MULTI>
 __device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
-  int bo, co; long long bi, ci;
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, co, ci);
-  atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
-  atomicAdd(ptr_upd<MULTI>(p, co) + ci, pack_delta(-1, -(long long)d));
+  atomicAdd(at_upd<MULTI>(p, best), pack_delta(1, (long long)d));
+  atomicAdd(at_upd<MULTI>(p, cc), pack_delta(-1, -(long long)d));
 }
 
 // generic in-place reduction of one vertex's staged segment (any degree <= kECap), unit weights
@@ -504,13 +526,10 @@ __device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_com
 
 template <bool MULTI>
 __device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int best, double vdeg) {
-  int bo, co; long long bi, ci;
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, co, ci);
-  atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
-  atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
-  atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, co) + ci), ~0ULL);
-  atomicAdd(ptr_udeg<MULTI>(p, co) + ci, -vdeg);
+  atomicAdd((unsigned long long *)at_usize<MULTI>(p, best), 1ULL);
+  atomicAdd(at_udeg<MULTI>(p, best), vdeg);
+  atomicAdd((unsigned long long *)at_usize<MULTI>(p, cc), ~0ULL);
+  atomicAdd(at_udeg<MULTI>(p, cc), -vdeg);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -595,16 +614,14 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     const int o0 = mine ? (int)(r0 - E0) : 0;
     int cc = 0, best = 0;
     if (mine) { cc = __ldg(p.cur + v); best = cc; }
-    int owner = 0; long long idx = 0;
     double cc_deg = 0.0, vdeg = 0.0, sl = 0.0;
     if (d) {
-      locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
       if (UNIT) {
-        cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
+        cc_deg = (double)__ldg(at_cdeg<MULTI>(p, cc));
         vdeg = (double)d;
         sl = p.has_self ? (double)__ldg(p.self_i + v) : 0.0;
       } else {
-        cc_deg = __ldg(&(ptr_cinfo_w<MULTI>(p, owner) + idx)->degree);
+        cc_deg = __ldg(&at_cinfo_w<MULTI>(p, cc)->degree);
         vdeg = __ldg(p.vdeg + v);
         sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
       }
@@ -633,13 +650,12 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     for (;;) {
       const bool has = m > 0;
       if (!__any_sync(0xffffffffu, has)) break;
-      int ck1 = 0, yo = 0; long long yi = 0;
+      int ck1 = 0;
       double ay1 = 0.0;
       if (has) {
         ck1 = s_comm[o0];
-        locate_impl<MULTI>(p.pt, p.base, p.lnv, ck1, yo, yi);
-        if (UNIT) ay1 = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
-        else ay1 = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
+        if (UNIT) ay1 = (double)__ldg(at_cdeg<MULTI>(p, ck1));
+        else ay1 = __ldg(&at_cinfo_w<MULTI>(p, ck1)->degree);
       }
       int ck2 = -1, c1 = 0, c2 = 0, m2 = 0;
       double sum1 = 0.0, sum2 = 0.0;
@@ -662,10 +678,9 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
         const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant);
         if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
         if (ck2 >= 0) {
-          locate_impl<MULTI>(p.pt, p.base, p.lnv, ck2, yo, yi);
           double ay2;
-          if (UNIT) { ay2 = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi); sum2 = (double)c2; }
-          else ay2 = __ldg(&(ptr_cinfo_w<MULTI>(p, yo) + yi)->degree);
+          if (UNIT) { ay2 = (double)__ldg(at_cdeg<MULTI>(p, ck2)); sum2 = (double)c2; }
+          else ay2 = __ldg(&at_cinfo_w<MULTI>(p, ck2)->degree);
           const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant);
           if (better_l<MULTI>(p, g2, ck2, bg, best, lbest)) { bg = g2; best = ck2; }
         }
@@ -673,15 +688,13 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
     }
     if (mine) {
       if (d && label_greater<MULTI>(p, best, lbest, cc)) {                   // singleton veto, dspl.hpp:224-225
-        int bo; long long bi;
-        locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
         long long sz_cc, sz_b;
         if (UNIT) {
-          sz_cc = __ldg(ptr_csize<MULTI>(p, owner) + idx);
-          sz_b = __ldg(ptr_csize<MULTI>(p, bo) + bi);
+          sz_cc = __ldg(at_csize<MULTI>(p, cc));
+          sz_b = __ldg(at_csize<MULTI>(p, best));
         } else {
-          sz_cc = __ldg(&(ptr_cinfo_w<MULTI>(p, owner) + idx)->size);
-          sz_b = __ldg(&(ptr_cinfo_w<MULTI>(p, bo) + bi)->size);
+          sz_cc = __ldg(&at_cinfo_w<MULTI>(p, cc)->size);
+          sz_b = __ldg(&at_cinfo_w<MULTI>(p, best)->size);
         }
         if (sz_cc == 1 && sz_b == 1) best = cc;
       }

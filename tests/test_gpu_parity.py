@@ -244,3 +244,25 @@ def test_upload_formats_agree(gpu, golden):
     nv, parts, rowptr, edges = as_single(case)
     res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=1)
     assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + 16 * len(edges) and res["timings"]["unit_weight"] == 0
+
+
+def test_full_size_config3_random_edges(gpu):
+    """BASELINE.json configs[2]: RGG -n 16777216 -p 2 (2 % random long edges, fixed documented seed) on one GPU, against
+    the golden trace of the unmodified reference on the same graph file (tools/make_fullsize_golden.py ... 2)."""
+    import json
+    import os
+    from minivite_b200 import hostgraph as hg
+    from oracle import oracle as O
+    path = os.path.join(os.path.dirname(__file__), "golden", "golden_full_16777216_p1_r2.json")
+    if not os.path.exists(path):
+        pytest.skip("config-3 golden not generated yet")
+    gold = json.load(open(path))
+    ss = hg.generate_rgg(gold["nv"], 1, random_edge_percent=gold["random_edge_percent"])
+    sh = ss.shards[0]
+    assert sh.lne == gold["ne"]
+    res = run_single(gpu, sh.parts, sh.rowptr, sh.edges, gold["nv"])
+    assert res["iters"] == gold["iters"] and repr(res["modularity"]) == repr(float(gold["modularity"]))
+    for t, g in zip(res["trace"], gold["trace"]):
+        assert float(t["modularity"]) == float(g["modularity"]) and int(t["moved"]) == g["moved"]
+        assert int(t["chash"]) == int(g["chash"], 16)
+    assert "%016x" % O.comm_hash(0, res["comm"]) == gold["final_chash"]
