@@ -82,6 +82,13 @@ int mvgpu_upload_shard(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, 
 int mvgpu_attach_shard_device(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
                               const int64_t *d_edge_indices, const void *d_edge_list);
 
+/* Device-side GenerateRGG (graph.hpp:584-1213, default RNG, no -l / -p): builds this rank's strip of the graph
+ * `miniVite -n nv_global` creates on nranks ranks directly in HBM, bit-identical to the reference generator, and
+ * attaches it as the context's shard.  unit_weight = 0 gives Euclidean edge weights (-w).  *lne_out: local edges. */
+int mvgpu_generate_rgg_shard(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int64_t *lne_out);
+/* Copy the shard's reference-format arrays (lnv+1 offsets, lne 16-byte records) back to the host. */
+int mvgpu_download_shard(mvgpu_ctx *ctx, int64_t *edge_indices, void *edge_list);
+
 /* ---- the Louvain phase (dspl.hpp:1280-1441) --------------------------------------------------- */
 /* lower/thresh as in the reference (main.cpp:149,70); *iters counts the rejected last iteration
  * (dspl.hpp:1430); *modularity is prevMod (dspl.hpp:1440).  Collective over all ranks. */

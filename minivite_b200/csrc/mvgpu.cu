@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cub/cub.cuh>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -25,6 +26,7 @@
 #include "../../include/mvgpu.h"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
+#include "rgg_gpu.cuh"
 
 namespace {
 
@@ -90,6 +92,8 @@ struct mvgpu_ctx {
   const Edge16 *d_edges = nullptr;
   DevBuf<long long> in_rowptr;
   DevBuf<Edge16> in_edges;
+  DevBuf<long long> gen_rowptr;       // device-generated RGG shard (mvgpu_generate_rgg_shard)
+  DevBuf<Edge16> gen_edges;
   // compact upload format (unit-weight shards): int32 global tails, staged through pinned chunks
   DevBuf<int32_t> in_tails32;
   DevBuf<long long> wide;
@@ -860,6 +864,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->in_tails32.release(); c->wide.release();
   for (int b = 0; b < 2; b++) if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
+  c->gen_rowptr.release(); c->gen_edges.release();
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
@@ -1003,6 +1008,104 @@ int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *pa
   c->d_tails32 = nullptr;
   c->h2d_bytes = 0;
   c->h2d_s = 0.0;
+  return 0;
+}
+
+// ---- section 8(f) rank 1: the reference's GenerateRGG on the device (rgg_gpu.cuh) ---------------------------------
+int mvgpu_generate_rgg_shard(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int64_t *lne_out) {
+  if (!c) return fail("null ctx");
+  CK(cudaSetDevice(c->device));
+  const int p = c->nranks, r = c->rank;
+  if (nv_global < 1 || nv_global % p != 0) return fail("[ERROR] Number of vertices must be perfectly divisible by number of processes.");
+  if (p & (p - 1)) return fail("[ERROR] Number of processes must be a power of 2.");
+  RggParams P;
+  memset(&P, 0, sizeof P);
+  P.n = nv_global / p; P.rank = r; P.nranks = p;
+  {                                                    // utils.hpp:91-98 reseeder(1)
+    std::seed_seq seq({1u});
+    std::vector<std::uint32_t> seeds(1);
+    seq.generate(seeds.begin(), seeds.end());
+    P.seed = (unsigned int)seeds[0];
+  }
+  const double rc = std::sqrt((double)std::log((double)nv_global) / (double)(3.14159 * nv_global));   // graph.hpp:629-631, PI of utils.hpp:44
+  const double rt = std::sqrt((double)2.0736 / (double)nv_global);
+  P.rn = (rc + rt) / 2.0;
+  P.rec_np = (double)(1.0 / (double)p);
+  if (!(P.rec_np > P.rn)) return fail("RGG radius does not fit the strip height (1/p > rn violated)");
+  {                                                    // divisor of std::generate_canonical<double,53>(minstd_rand0)
+    const long double rr = 2147483646.0L;
+    double tmp = 1.0;
+    tmp *= rr;
+    P.r_range = tmp;
+    tmp *= rr;
+    P.r_range2 = tmp;
+  }
+  long long ncell = (long long)std::floor(1.0 / P.rn);
+  while (ncell > 1 && 1.0 / (double)ncell < P.rn * 1.000001) ncell--;
+  if (ncell < 1) ncell = 1;
+  P.ncell = ncell;
+  P.ylo = r * P.rec_np - P.rn * 1.01;
+  P.yhi = (r + 1) * P.rec_np + P.rn * 1.01;
+  auto cell_of_h = [&](double v) { long long q = (long long)std::floor(v * (double)ncell); return q < 0 ? 0LL : (q >= ncell ? ncell - 1 : q); };
+  const long long row0 = std::max<long long>(0, cell_of_h(P.ylo) - 1), row1 = std::min<long long>(ncell - 1, cell_of_h(P.yhi) + 1);
+  P.row0 = row0; P.nrows = row1 - row0 + 1;
+  const long long ncells = P.nrows * ncell;
+  if (ncells + 1 >= (1LL << 31) || P.n >= (1LL << 31)) return fail("RGG too large for the device generator");
+  cudaStream_t s = c->stream;
+  const int nsm = c->num_sms;
+  DevBuf<double> X, UY, cx, cy;
+  DevBuf<long long> cgid, deg;
+  DevBuf<unsigned int> cnt, cstart;
+  TRY(X.ensure(P.n)); TRY(UY.ensure(P.n)); TRY(cnt.ensure(ncells + 1)); TRY(cstart.ensure(ncells + 1)); TRY(deg.ensure(P.n + 1));
+  k_rgg_points<<<grid_for(P.n, 256, nsm), 256, 0, s>>>(P, X.p, UY.p);
+  CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned int) * (ncells + 1), s));
+  k_rgg_bin<<<grid_for(P.n, 256, nsm), 256, 0, s>>>(P, X.p, UY.p, 0, cnt.p, nullptr, nullptr, nullptr, nullptr);
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, cstart.p, (int)(ncells + 1), s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, cnt.p, cstart.p, (int)(ncells + 1), s));
+  unsigned int ncand = 0;
+  CK(cudaMemcpyAsync(&ncand, cstart.p + ncells, sizeof ncand, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  TRY(cx.ensure(ncand)); TRY(cy.ensure(ncand)); TRY(cgid.ensure(ncand));
+  CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned int) * (ncells + 1), s));
+  k_rgg_bin<<<grid_for(P.n, 256, nsm), 256, 0, s>>>(P, X.p, UY.p, 1, cnt.p, cstart.p, cx.p, cy.p, cgid.p);
+  CK(cudaMemsetAsync(deg.p + P.n, 0, sizeof(long long), s));
+  k_rgg_neighbours<false><<<grid_for(P.n, 128, nsm, 16), 128, 0, s>>>(P, X.p, UY.p, cstart.p, cx.p, cy.p, cgid.p, unit_weight, deg.p, nullptr);
+  TRY(c->gen_rowptr.ensure(P.n + 1));
+  tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, deg.p, c->gen_rowptr.p, (int)(P.n + 1), s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, deg.p, c->gen_rowptr.p, (int)(P.n + 1), s));
+  long long lne = 0;
+  CK(cudaMemcpyAsync(&lne, c->gen_rowptr.p + P.n, sizeof lne, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  TRY(c->gen_edges.ensure(lne));
+  k_rgg_neighbours<true><<<grid_for(P.n, 128, nsm, 16), 128, 0, s>>>(P, X.p, UY.p, cstart.p, cx.p, cy.p, cgid.p, unit_weight, c->gen_rowptr.p, c->gen_edges.p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  X.release(); UY.release(); cx.release(); cy.release(); cgid.release(); deg.release(); cnt.release(); cstart.release();
+  std::vector<int64_t> parts(p + 1);
+  for (int q = 0; q <= p; q++) parts[q] = (nv_global * q) / p;
+  TRY(set_graph(c, nv_global, parts.data(), P.n, lne));
+  c->d_rowptr64 = c->gen_rowptr.p;
+  c->d_edges = c->gen_edges.p;
+  c->d_tails32 = nullptr;
+  c->h2d_bytes = 0;
+  c->h2d_s = 0.0;
+  if (lne_out) *lne_out = lne;
+  return 0;
+}
+
+int mvgpu_download_shard(mvgpu_ctx *c, int64_t *edge_indices, void *edge_list) {
+  if (!c || !c->have_graph || !c->d_rowptr64) return fail("no shard on the device");
+  if (!c->d_edges) return fail("the shard was uploaded in the compact format; nothing to download");
+  CK(cudaSetDevice(c->device));
+  if (edge_indices) CK(cudaMemcpyAsync(edge_indices, c->d_rowptr64, sizeof(long long) * (c->lnv + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (edge_list && c->lne) CK(cudaMemcpyAsync(edge_list, c->d_edges, sizeof(Edge16) * c->lne, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

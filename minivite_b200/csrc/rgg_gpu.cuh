@@ -1,0 +1,139 @@
+// Device-side random geometric graph generator: SURVEY.md section 8(f) rank 1, the step *before* the Louvain path.
+//
+// Builds strip `rank` of the graph `miniVite -n nv` creates on `nranks` ranks (reference GenerateRGG,
+// graph.hpp:584-1213, default RNG path, no -l / -p) directly in HBM, in the reference's own array format
+// (int64 rowptr[lnv+1], {int64 tail; double weight}[lne]), bit-identical to the reference generator and to this
+// repo's host generator (host/rgg.hpp):
+//   * coordinates: minstd_rand0 (x <- 16807 x mod 2^31-1) seeded with reseeder(1); vertex i consumes outputs
+//     4i+1..4i+4 (two per double, std::generate_canonical<double,53>); every strip restarts from the same seed
+//     (graph.hpp:680-700).  The generator is a pure multiplicative LCG, so thread i jumps to its position with one
+//     modular power instead of replaying the stream;
+//   * radius and predicate: rn of graph.hpp:629-631, sqrt(dx*dx+dy*dy) <= rn in fp64 with explicit _rn operations
+//     (no FMA contraction), pairs between adjacent strips skipped when the local indices are equal
+//     (graph.hpp:817,849);
+//   * uniform cell grid (cell width >= rn) instead of the reference's O((n/p)^2) loops; adjacency sorted by tail
+//     (graph.hpp:1145-1153).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace mv {
+
+struct RggParams {
+  long long n;               // vertices per strip
+  int rank, nranks;
+  unsigned int seed;         // (unsigned)reseeder(1)
+  double rn;                 // radius
+  double rec_np;             // 1/nranks as the reference computes it
+  double r_range;            // 2147483646.0  (urng.max() - urng.min() + 1)
+  double r_range2;           // (double)(r_range * r_range evaluated in long double), the divisor of generate_canonical
+  long long ncell;           // cells per unit length
+  long long row0, nrows;     // slab of cell rows this strip can reach
+  double ylo, yhi;           // candidate band
+};
+
+__device__ __forceinline__ unsigned long long mulmod31(unsigned long long a, unsigned long long b) {
+  return (a * b) % 2147483647ULL;
+}
+__device__ __forceinline__ unsigned long long powmod31(unsigned long long a, unsigned long long e) {
+  unsigned long long r = 1;
+  while (e) { if (e & 1) r = mulmod31(r, a); a = mulmod31(a, a); e >>= 1; }
+  return r;
+}
+// std::generate_canonical<double,53>(minstd_rand0): two draws; sum and divisor rounded exactly as libstdc++ does
+__device__ __forceinline__ double canonical2(unsigned long long o1, unsigned long long o2, const RggParams &p) {
+  double sum = (double)(o1 - 1ULL);                                   // * tmp (= 1.0)
+  sum = __dadd_rn(sum, __dmul_rn((double)(o2 - 1ULL), p.r_range));
+  double ret = __ddiv_rn(sum, p.r_range2);
+  if (ret >= 1.0) ret = 0.99999999999999988898;                       // nextafter(1.0, 0.0)
+  return ret;
+}
+// canonical X and canonical Y of local index i (identical for every strip)
+__device__ __forceinline__ void point_canon(long long i, const RggParams &p, double &ux, double &uy) {
+  unsigned long long x0 = (unsigned long long)p.seed % 2147483647ULL;
+  if (x0 == 0) x0 = 1;
+  unsigned long long x = mulmod31(x0, powmod31(16807ULL, (unsigned long long)(4 * i)));
+  const unsigned long long o1 = mulmod31(x, 16807ULL), o2 = mulmod31(o1, 16807ULL), o3 = mulmod31(o2, 16807ULL),
+                           o4 = mulmod31(o3, 16807ULL);
+  ux = canonical2(o1, o2, p);
+  uy = canonical2(o3, o4, p);
+}
+__device__ __forceinline__ double strip_y(double uy, int s, const RggParams &p) {
+  const double lo = __dmul_rn((double)s, p.rec_np), hi = __dadd_rn(lo, p.rec_np);
+  return __dadd_rn(__dmul_rn(uy, __dsub_rn(hi, lo)), lo);           // uniform_real_distribution: u*(b-a)+a
+}
+__device__ __forceinline__ long long cell_of(double v, long long ncell) {
+  long long c = (long long)floor(__dmul_rn(v, (double)ncell));
+  return c < 0 ? 0 : (c >= ncell ? ncell - 1 : c);
+}
+
+// X (shared by all strips) and canonical Y
+__global__ void __launch_bounds__(256) k_rgg_points(RggParams p, double *X, double *UY) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    double ux, uy;
+    point_canon(i, p, ux, uy);
+    X[i] = __dadd_rn(__dmul_rn(ux, 1.0), 0.0);
+    UY[i] = uy;
+  }
+}
+
+// candidates = all points of the own strip + the points of the adjacent strips inside the band [ylo, yhi];
+// pass 0 counts per cell, pass 1 scatters (cell-sorted arrays cx, cy, cgid)
+__global__ void __launch_bounds__(256) k_rgg_bin(RggParams p, const double *X, const double *UY, int pass, unsigned int *cell_cnt,
+                                                 const unsigned int *cell_start, double *cx, double *cy, long long *cgid) {
+  const int s0 = max(0, p.rank - 1), s1 = min(p.nranks - 1, p.rank + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const double x = X[i], uy = UY[i];
+    for (int s = s0; s <= s1; s++) {
+      const double y = strip_y(uy, s, p);
+      if (y < p.ylo || y > p.yhi) continue;
+      const long long row = cell_of(y, p.ncell);
+      if (row < p.row0 || row >= p.row0 + p.nrows) continue;
+      const long long c = (row - p.row0) * p.ncell + cell_of(x, p.ncell);
+      if (pass == 0) atomicAdd(&cell_cnt[c], 1u);
+      else {
+        const unsigned int pos = cell_start[c] + atomicAdd(&cell_cnt[c], 1u);
+        cx[pos] = x; cy[pos] = y; cgid[pos] = (long long)s * p.n + i;
+      }
+    }
+  }
+}
+
+// neighbours of local vertex i: pass 0 counts (deg), pass 1 writes {tail, weight} records, then sorts them by tail
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_rgg_neighbours(RggParams p, const double *X, const double *UY, const unsigned int *cell_start,
+                                                        const double *cx, const double *cy, const long long *cgid, int unit,
+                                                        long long *deg_or_rowptr, Edge16 *edges) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const double xi = X[i], yi = strip_y(UY[i], p.rank, p);
+    const long long row = cell_of(yi, p.ncell), col = cell_of(xi, p.ncell);
+    const long long c0 = max(0LL, col - 1), c1 = min(p.ncell - 1, col + 1);
+    long long cnt = 0;
+    Edge16 *out = FILL ? edges + deg_or_rowptr[i] : nullptr;
+    for (long long rr = max(p.row0, row - 1); rr <= min(p.row0 + p.nrows - 1, row + 1); rr++) {
+      const unsigned int b = cell_start[(rr - p.row0) * p.ncell + c0], e = cell_start[(rr - p.row0) * p.ncell + c1 + 1];
+      for (unsigned int k = b; k < e; k++) {
+        const double dx = __dsub_rn(xi, cx[k]), dy = __dsub_rn(yi, cy[k]);
+        const double ed = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        if (!(ed <= p.rn)) continue;
+        const long long g = cgid[k];
+        if (g % p.n == i) continue;          // the vertex itself, or the equal-index vertex of an adjacent strip
+        if (FILL) { out[cnt].tail = g; out[cnt].weight = unit ? 1.0 : ed; }
+        cnt++;
+      }
+    }
+    if (!FILL) deg_or_rowptr[i] = cnt;
+    else {
+      for (long long a = 1; a < cnt; a++) {              // insertion sort by tail (a few dozen entries at most)
+        const Edge16 key = out[a];
+        long long b2 = a - 1;
+        while (b2 >= 0 && out[b2].tail > key.tail) { out[b2 + 1] = out[b2]; b2--; }
+        out[b2 + 1] = key;
+      }
+    }
+  }
+}
+
+}  // namespace mv

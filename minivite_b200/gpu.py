@@ -27,7 +27,8 @@ class Timings(ctypes.Structure):
 
 
 EXPORTS = ["mvgpu_last_error", "mvgpu_device_count", "mvgpu_create", "mvgpu_destroy", "mvgpu_get_unique_id",
-           "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_louvain",
+           "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_generate_rgg_shard",
+           "mvgpu_download_shard", "mvgpu_louvain",
            "mvgpu_get_communities", "mvgpu_get_communities_device", "mvgpu_set_option", "mvgpu_get_trace",
            "mvgpu_get_timings", "mvgpu_get_scan_times", "mvgpu_get_constant", "mvgpu_get_shard_info", "mvgpu_dist_louvain_method"]
 
@@ -50,6 +51,8 @@ def lib():
         L.mvgpu_comm_init.argtypes = [vp, vp]
         L.mvgpu_upload_shard.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.mvgpu_attach_shard_device.argtypes = [vp, i64, vp, i64, i64, vp, vp]
+        L.mvgpu_generate_rgg_shard.argtypes = [vp, i64, ci, ctypes.POINTER(i64)]
+        L.mvgpu_download_shard.argtypes = [vp, vp, vp]
         L.mvgpu_louvain.argtypes = [vp, dbl, dbl, ctypes.POINTER(ci), ctypes.POINTER(dbl)]
         L.mvgpu_get_communities.argtypes = [vp, vp]
         L.mvgpu_get_communities_device.argtypes = [vp, ctypes.POINTER(vp)]
@@ -120,6 +123,22 @@ class LouvainGPU:
                                             ctypes.c_void_p(d_rowptr_ptr), ctypes.c_void_p(d_edges_ptr)))
         self.lnv = int(lnv)
         self._keep = keepalive
+
+    def generate_rgg(self, nv_global, unit_weight=True):
+        """Build this rank's strip of `miniVite -n nv_global` on the device (reference GenerateRGG); returns lne."""
+        lne = ctypes.c_int64(0)
+        _ck(lib().mvgpu_generate_rgg_shard(self._h, int(nv_global), int(bool(unit_weight)), ctypes.byref(lne)))
+        self.lnv = int(nv_global) // self.nranks
+        self._lne = lne.value
+        return lne.value
+
+    def download_shard(self):
+        """The shard's reference-format arrays (int64 rowptr, {tail, weight} records) as numpy arrays."""
+        info = self.shard_info()
+        rowptr = np.zeros(info["lnv"] + 1, dtype=np.int64)
+        edges = np.zeros(info["lne"], dtype=np.dtype([("tail", "<i8"), ("weight", "<f8")]))
+        _ck(lib().mvgpu_download_shard(self._h, rowptr.ctypes.data, edges.ctypes.data if info["lne"] else None))
+        return rowptr, edges
 
     def set_option(self, name, value):
         _ck(lib().mvgpu_set_option(self._h, name.encode(), int(value)))
