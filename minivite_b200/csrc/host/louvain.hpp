@@ -2,8 +2,10 @@
 // same return value / `iters` semantics; the body marshals the Graph's arrays across the C ABI
 // (include/mvgpu.h) to the CUDA library instead of running the OpenMP/MPI loops.
 #pragma once
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -56,6 +58,40 @@ inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph
   }
   if (rc.comm_out) {
     rc.comm_out->resize(dg.get_lnv());
+    if (mvgpu_get_communities(ctx, rc.comm_out->data())) mv_abort("mvgpu_get_communities");
+  }
+  mvgpu_destroy(ctx);
+  return mod;
+}
+
+// Variant for `-D`: the shard never exists on the host -- GenerateRGG runs on the device (mvgpu_generate_rgg_shard,
+// the reference's generator of graph.hpp:584-1213 bit for bit) and the Louvain phase consumes it in place.
+// `gen_seconds` receives the generation time, `lne` the local edge count.
+inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, const GraphElem nv, const bool unitEdgeWeight,
+                                                const GraphWeight lower, const GraphWeight thresh, int &iters,
+                                                GpuRankContext &rc, GraphElem &lne, double &gen_seconds,
+                                                const std::function<void()> &before_louvain) {
+  mvgpu_ctx *ctx = nullptr;
+  if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
+  if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
+  if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
+  const auto t0 = std::chrono::steady_clock::now();
+  int64_t lne64 = 0;
+  if (mvgpu_generate_rgg_shard(ctx, nv, unitEdgeWeight ? 1 : 0, &lne64)) mv_abort("mvgpu_generate_rgg_shard");
+  gen_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  lne = lne64;
+  before_louvain();
+  double mod = 0.0;
+  if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
+  mvgpu_get_timings(ctx, &rc.timings);
+  if (rc.trace) {
+    int n = 0;
+    mvgpu_get_trace(ctx, 0, nullptr, &n);
+    rc.iter_trace.resize(n);
+    if (n) mvgpu_get_trace(ctx, n, rc.iter_trace.data(), &n);
+  }
+  if (rc.comm_out) {
+    rc.comm_out->resize(nv / nprocs);
     if (mvgpu_get_communities(ctx, rc.comm_out->data())) mv_abort("mvgpu_get_communities");
   }
   mvgpu_destroy(ctx);

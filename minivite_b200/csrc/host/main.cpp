@@ -7,6 +7,7 @@
 //   -t <thr>   convergence threshold      -n <nv> generate an RGG          -w  Euclidean edge weights
 //   -l         LCG random numbers         -p <pct> extra random edges      -s  print the graph
 // additions: -g <gpus> (default 1)   -o <prefix> dump final communities per rank   -T per-iteration trace on stderr
+//            -D generate the RGG on the GPU (same graph; with -n, without -l/-p/-s)
 #include <getopt.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -30,7 +31,7 @@ static std::string inputFileName, dumpPrefix;
 static int me = 0, nprocs = 1;
 static int ranksPerNode = 1;
 static GraphElem nvRGG = 0;
-static bool generateGraph = false, readBalanced = false, showGraph = false, traceIters = false;
+static bool generateGraph = false, readBalanced = false, showGraph = false, traceIters = false, deviceGenerate = false;
 static GraphWeight randomEdgePercent = 0.0;
 static bool randomNumberLCG = false, isUnitEdgeWeight = true;
 static GraphWeight threshold = 1.0E-6;
@@ -79,7 +80,7 @@ static long long reduce_sum_ll(long long v) {
 
 static void parseCommandLine(const int argc, char *const argv[]) {
   int ret;
-  while ((ret = getopt(argc, argv, "f:br:t:n:wlp:sg:o:T")) != -1) {
+  while ((ret = getopt(argc, argv, "f:br:t:n:wlp:sg:o:TD")) != -1) {
     switch (ret) {
       case 'f': inputFileName.assign(optarg); break;
       case 'b': readBalanced = true; break;
@@ -93,6 +94,7 @@ static void parseCommandLine(const int argc, char *const argv[]) {
       case 'g': nprocs = atoi(optarg); break;
       case 'o': dumpPrefix.assign(optarg); break;
       case 'T': traceIters = true; break;
+      case 'D': deviceGenerate = true; break;
       default: assert(0 && "Option not recognized!!!"); break;
     }
   }
@@ -113,6 +115,9 @@ static void parseCommandLine(const int argc, char *const argv[]) {
     std::cerr << "Invalid random edge percentage for generated graph!" << std::endl; exit(99);
   }
   if (nprocs < 1 || nprocs > 16) { std::cerr << "Invalid number of GPUs (-g)." << std::endl; exit(99); }
+  if (deviceGenerate && (!generateGraph || randomNumberLCG || randomEdgePercent > 0.0 || showGraph)) {
+    std::cerr << "-D (generate the RGG on the GPU) needs -n and excludes -l, -p and -s." << std::endl; exit(99);
+  }
 }
 
 int main(int argc, char *argv[]) {
@@ -130,9 +135,35 @@ int main(int argc, char *argv[]) {
     if (p == 0) { me = r; break; }
   }
 
+  // the reference prints these with -DPRINT_DIST_STATS (its Makefile default, Makefile:10-16)
+  auto print_stats = [&](long lne, GraphElem nv, GraphElem ne) {
+    const double sumdeg = reduce_sum((double)lne), sum_sq = reduce_sum((double)lne * (double)lne);
+    shm->i64[32 + me] = lne;
+    rank_barrier();
+    if (me == 0) {
+      long maxdeg = 0;
+      for (int r = 0; r < nprocs; r++) maxdeg = std::max<long>(maxdeg, shm->i64[32 + r]);
+      const double average = sumdeg / nprocs, avg_sq = sum_sq / nprocs, var = avg_sq - average * average;
+      std::cout << std::endl;
+      std::cout << "-------------------------------------------------------" << std::endl;
+      std::cout << "Graph edge distribution characteristics" << std::endl;
+      std::cout << "-------------------------------------------------------" << std::endl;
+      std::cout << "Number of vertices: " << nv << std::endl;
+      std::cout << "Number of edges: " << ne << std::endl;
+      std::cout << "Maximum number of edges: " << maxdeg << std::endl;
+      std::cout << "Average number of edges: " << average << std::endl;
+      std::cout << "Expected value of X^2: " << avg_sq << std::endl;
+      std::cout << "Variance: " << var << std::endl;
+      std::cout << "Standard deviation: " << std::sqrt(var) << std::endl;
+      std::cout << "-------------------------------------------------------" << std::endl;
+    }
+    rank_barrier();
+  };
+
   rank_barrier();
   const double td0 = wtime();
   Graph *g = nullptr;
+  if (!deviceGenerate) {
   try {
     if (generateGraph) {
       mvhost::GenerateRGG gr(nvRGG, nprocs);
@@ -159,36 +190,14 @@ int main(int argc, char *argv[]) {
   if (showGraph) {
     for (int p = 0; p < nprocs; p++) { rank_barrier(); if (p == me) g->print(); }
   }
-  {  // the reference prints these with -DPRINT_DIST_STATS (its Makefile default, Makefile:10-16)
-    const long lne = (long)g->get_lne();
-    const double sumdeg = reduce_sum((double)lne), sum_sq = reduce_sum((double)lne * (double)lne);
-    shm->i64[32 + me] = lne;
-    rank_barrier();
-    if (me == 0) {
-      long maxdeg = 0;
-      for (int r = 0; r < nprocs; r++) maxdeg = std::max<long>(maxdeg, shm->i64[32 + r]);
-      const double average = sumdeg / nprocs, avg_sq = sum_sq / nprocs, var = avg_sq - average * average;
-      std::cout << std::endl;
-      std::cout << "-------------------------------------------------------" << std::endl;
-      std::cout << "Graph edge distribution characteristics" << std::endl;
-      std::cout << "-------------------------------------------------------" << std::endl;
-      std::cout << "Number of vertices: " << g->get_nv() << std::endl;
-      std::cout << "Number of edges: " << g->get_ne() << std::endl;
-      std::cout << "Maximum number of edges: " << maxdeg << std::endl;
-      std::cout << "Average number of edges: " << average << std::endl;
-      std::cout << "Expected value of X^2: " << avg_sq << std::endl;
-      std::cout << "Variance: " << var << std::endl;
-      std::cout << "Standard deviation: " << std::sqrt(var) << std::endl;
-      std::cout << "-------------------------------------------------------" << std::endl;
-    }
-    rank_barrier();
-  }
+  print_stats((long)g->get_lne(), g->get_nv(), g->get_ne());
   const double tdt = reduce_sum(wtime() - td0);
   if (me == 0) {
     if (!generateGraph)
       std::cout << "Time to read input file and create distributed graph (in s): " << (tdt / nprocs) << std::endl;
     else
       std::cout << "Time to generate distributed graph of " << nvRGG << " vertices (in s): " << (tdt / nprocs) << std::endl;
+  }
   }
 
   // ---- communicator bootstrap (stands in for MPI_Init + createCommunityMPIType, main.cpp:78-102)
@@ -211,9 +220,27 @@ int main(int argc, char *argv[]) {
   size_t ssz = 0, rsz = 0;
   int iters = 0;
 
-  rank_barrier();
-  const double t1 = wtime();
-  currMod = distLouvainMethod(me, nprocs, *g, ssz, rsz, ssizes, rsizes, svdata, rvdata, currMod, threshold, iters, rc);
+  GraphElem nv_rep = 0, ne_rep = 0, base_rep = 0, lnv_rep = 0;
+  double t1 = 0.0;
+  if (deviceGenerate) {
+    GraphElem lne = 0;
+    double gen_s = 0.0;
+    currMod = distLouvainMethodOnDeviceRGG(me, nprocs, nvRGG, isUnitEdgeWeight, currMod, threshold, iters, rc, lne, gen_s, [&]() {
+      ne_rep = reduce_sum_ll(lne);                 // between generation and the Louvain phase: the reference's report + timer start
+      print_stats((long)lne, nvRGG, ne_rep);
+      const double tdt = reduce_sum(gen_s);
+      if (me == 0)
+        std::cout << "Time to generate distributed graph of " << nvRGG << " vertices (in s): " << (tdt / nprocs) << std::endl;
+      rank_barrier();
+      t1 = wtime();
+    });
+    nv_rep = nvRGG; lnv_rep = nvRGG / nprocs; base_rep = lnv_rep * me;
+  } else {
+    rank_barrier();
+    t1 = wtime();
+    currMod = distLouvainMethod(me, nprocs, *g, ssz, rsz, ssizes, rsizes, svdata, rvdata, currMod, threshold, iters, rc);
+    nv_rep = g->get_nv(); ne_rep = g->get_ne(); base_rep = g->get_base(me); lnv_rep = g->get_lnv();
+  }
   rank_barrier();
   const double total = wtime() - t1;
   const double tot_time = reduce_sum(total);
@@ -226,7 +253,7 @@ int main(int argc, char *argv[]) {
   if (!dumpPrefix.empty()) {
     const std::string fn = dumpPrefix + "." + std::to_string(me);
     FILE *f = fopen(fn.c_str(), "wb");
-    long long hdr[2] = {(long long)g->get_base(me), (long long)g->get_lnv()};
+    long long hdr[2] = {(long long)base_rep, (long long)lnv_rep};
     fwrite(hdr, 8, 2, f);
     fwrite(comm.data(), sizeof(GraphElem), comm.size(), f);
     fclose(f);
@@ -247,13 +274,13 @@ int main(int argc, char *argv[]) {
     std::cout << "-------------------------------------------------------" << std::endl;
     // additions of this build: device-side phase time (H2D upload excluded) and throughput
     std::cout << "GPU Louvain phase (in s), H2D upload (in s): " << avgd << ", " << rc.timings.h2d_s << std::endl;
-    std::cout << "Edges/s (ne*iters/t), s/iter: " << (double)g->get_ne() * iters / avgd << ", " << avgd / iters << std::endl;
+    std::cout << "Edges/s (ne*iters/t), s/iter: " << (double)ne_rep * iters / avgd << ", " << avgd / iters << std::endl;
     std::cout << "-------------------------------------------------------" << std::endl;
     fprintf(stderr, "RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d threads=0\n", currMod, iters, avgd,
-            (long)g->get_nv(), (long)g->get_ne(), nprocs);
+            (long)nv_rep, (long)ne_rep, nprocs);
   }
   rank_barrier();
-  delete g;
+  delete g;   // nullptr with -D
   fflush(stdout); fflush(stderr);
   if (me != 0) _exit(0);
   int st;

@@ -48,3 +48,13 @@ def test_cli_rejects_bad_options():
     assert p.returncode != 0 and "Must specify some options." in p.stderr
     p = subprocess.run([EXE, "-n", "1000", "-g", "3"], capture_output=True, text=True)
     assert p.returncode != 0
+
+
+def test_cli_device_generation(tmp_path, golden):
+    """-D: GenerateRGG runs on the GPU (mvgpu_generate_rgg_shard); same graph, same trace as the reference's `-n`."""
+    case = golden["rgg_n16384_p1"]
+    p = subprocess.run([EXE, "-n", "16384", "-T", "-D"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert f"Number of edges: {case['ne']}" in p.stdout
+    it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
+    assert [(float(a[1]), int(a[2]), a[3]) for a in it] == [(float(g["modularity"]), g["moved"], g["chash"]) for g in case["trace"]]

@@ -148,3 +148,8 @@ def test_cli_multi_gpu(tmp_path, golden):
     for (k, m, mv, h), g in zip(it, case["trace"]):
         assert float(m) == float(g["modularity"]) and int(mv) == g["moved"] and h == g["chash"]
     assert "Modularity, #Iterations: " in p.stdout
+    # same run with the graph generated on the GPUs (-D)
+    p = subprocess.run([exe, "-g", "2", "-n", "16384", "-T", "-D"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
+    assert len(it) == case["iters"] and it[-1][3] == case["trace"][-1]["chash"]
