@@ -54,9 +54,13 @@ int fail(const std::string &msg) { g_err = msg; return 1; }
   } while (0)
 
 template <typename T>
-struct DevBuf {              // grow-only device buffer (allocations are cached across runs)
+struct DevBuf {              // grow-only device buffer (allocations are cached across runs); frees itself
   T *p = nullptr;
   size_t cap = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { release(); }
   int ensure(size_t n) {
     if (n <= cap && p) return 0;
     if (p) cudaFree(p);
