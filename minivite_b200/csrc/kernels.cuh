@@ -176,8 +176,10 @@ __device__ __forceinline__ void locate_remote(const PeerTable &pt, int y, int &o
 #define MV_AT(field, type)                                                                           \
   template <bool MULTI>                                                                              \
   __device__ __forceinline__ type at_##field(const ScanParams &p, int y) {                           \
+    /* single rank: signed 64-bit index, so the compiler can fold "- base" into the array pointer */ \
+    if (!MULTI) return p.loc_##field + ((long long)y - p.base);                                      \
     const unsigned int i = (unsigned int)(y - (int)p.base);                                          \
-    if (!MULTI || i < (unsigned int)p.lnv) return p.loc_##field + i;                                 \
+    if (i < (unsigned int)p.lnv) return p.loc_##field + i;                                           \
     int o; long long idx;                                                                            \
     locate_remote(p.pt, y, o, idx);                                                                  \
     return p.pt.field[o] + idx;                                                                      \
