@@ -110,6 +110,7 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "compact_upload" (1:
  * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 0 (default) = the 16-byte
  * records as they are), "host_threads" (OpenMP width of that host pass, default 8). */
+/* In a multi-rank run every rank must set the same options (they change which collectives a run issues). */
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
 int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);
 int mvgpu_get_timings(mvgpu_ctx *ctx, mvgpu_timings *out);
