@@ -1,5 +1,6 @@
 // Device kernels of the Louvain phase for sm_100a (B200).  Hand-written CUDA; no tensor cores: the
-// path is a sparse gather/scan, bound by L2/HBM sector throughput.
+// path is a sparse gather/scan.  With the reference's vertex numbering it is bound by HBM
+// sector throughput (random 4-byte gathers); after the locality renumbering below it is instruction-issue bound.
 //
 // Data layout in HBM (per rank/GPU; built once per run by the setup kernels from the reference-format
 // arrays int64 rowptr[lnv+1] + {int64 tail; double w}[lne]):
@@ -8,16 +9,18 @@
 //                                   (replaces the reference's per-edge owner test + unordered_map lookup,
 //                                   dspl.hpp:251-260)
 //   weights  double[lne]            only when some weight != 1.0
-//   cur/tgt  int32[lnv+nghost]      community (GLOBAL id) of every slot; ghosts are refreshed by the
+//   cur/tgt  int32[lnv+nghost]      community (global internal id) of every slot; ghosts are refreshed by the
 //                                   per-iteration exchange (dspl.hpp:559-688)
+//   lab      int32[lnv]             after renumbering: original global vertex id of every internal id (labels)
 //   unit-weight fast path (all weights 1, 2m < 2^31): Comm{size,degree} (dspl.hpp:61-66) as exact integers, SoA:
 //     cdeg   uint32[lnv]  community degree: the only field the gain needs (4 B gather per candidate)
 //     csize  int32[lnv]   community size: read only for the singleton veto (dspl.hpp:224-225)
 //     upd    uint64[lnv]  = dsize*2^32 + ddeg packed two's-complement delta: ONE 64-bit atomic per community
 //                           update (dspl.hpp:339-346); fold decodes it (dspl.hpp:458-471)
 //   weighted path: cinfo_w {int64 size; double degree}[lnv], usize int64[lnv], udeg double[lnv], vdeg double[lnv]
-// With 32-bit ids the randomly gathered arrays at 16M vertices are 64 MB (cur) + 64 MB (cdeg); `cur` gathers carry
-// an L2 evict_last policy and all streamed arrays evict_first so that the gather target stays L2 resident.
+// With 32-bit ids the gathered arrays at 16M vertices are 64 MB (cur) + 64 MB (cdeg).  L2 policy hints alone did
+// not keep them resident (measured); the renumbering makes the gathers local instead.  Streamed arrays (tails,
+// rowptr, target writes) still carry an L2 evict_first policy.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
