@@ -81,7 +81,10 @@ def check(res, case, exact=True):
 @pytest.mark.parametrize("case_name,world", [("rgg_n16384_p2", 2), ("file_rgg_n16384_s1_p2", 2), ("hand_path16_p2", 2),
                                              ("hand_clique_ring_p2", 2), ("hand_loops_multi_p2", 2), ("hand_k66_p2", 2),
                                              ("rgg_n16384_p4", 4), ("rgg_n131072_p8", 8), ("file_rgg_n32768_s8_p4", 4),
-                                             ("file_balanced_n16384_p2", 2), ("file_balanced_n16384_p4", 4)])
+                                             ("file_balanced_n16384_p2", 2), ("file_balanced_n16384_p4", 4),
+                                             # SURVEY.md 8(c) known answers of `miniVite -n 524288` (auto renumbering on)
+                                             ("file_rgg_n524288_s1_p1", 2), ("file_rgg_n524288_s8_p8", 2),
+                                             ("file_rgg_n524288_s8_p8", 8)])
 def test_multi_gpu_matches_reference_ranks(tmp_path, golden, case_name, world):
     if ngpus() < world:
         pytest.skip(f"needs {world} GPUs")

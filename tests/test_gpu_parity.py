@@ -231,8 +231,8 @@ def test_locality_renumbering_keeps_results(gpu, golden):
 
 
 def test_upload_formats_agree(gpu, golden):
-    """mvgpu_upload_shard narrows unit-weight shards to 4-byte tails on the host (compact_upload=1, default) or ships
-    the 16-byte records (0); weighted shards always take the full records.  Same results either way."""
+    """mvgpu_upload_shard narrows unit-weight shards to 4-byte tails on the host (compact_upload=1) or ships
+    the 16-byte records (0, default); weighted shards always take the full records.  Same results either way."""
     for name in ("rgg_n65536_p1", "hand_loops_multi_p1", "file_balanced_n16384_p4"):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)

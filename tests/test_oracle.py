@@ -18,6 +18,10 @@ def test_golden_file_has_all_kinds(golden):
     assert kinds == {"rgg", "file_rgg", "hand", "file_balanced"}
     assert golden["rgg_n16384_p1"]["modularity"] == "0.75671532450841406"   # SURVEY.md 8(c) known answer
     assert golden["rgg_n16384_p1"]["final_chash"] == "5bf1e47053c42601"
+    # `miniVite -n 524288` on 1 and 8 ranks (graph files written by our byte-identical generator)
+    c1, c8 = golden["file_rgg_n524288_s1_p1"], golden["file_rgg_n524288_s8_p8"]
+    assert (c1["ne"], c1["iters"], c1["modularity"]) == (4997382, 20, "0.75810023251607561")
+    assert (c8["ne"], c8["iters"], c8["modularity"]) == (5003290, 19, "0.75862461064860043")
 
 
 def test_oracle_matches_every_golden_case(golden):
