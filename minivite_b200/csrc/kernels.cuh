@@ -1263,7 +1263,7 @@ __global__ void k_p2p_allreduce(P2PPeers pp, unsigned long long epoch, const Acc
                                 unsigned long long *tr2) {
   const int t = threadIdx.x;
   P2PState *mine = pp.st[pp.rank];
-  const int par = (int)(epoch & 1);
+  const int par = (int)((epoch >> 1) & 1);        // epochs alternate barrier/allreduce: bit 1 flips per iteration
   if (t < pp.nranks) {
     const double le = unit ? (double)acc->le_u : acc->le_d, la2 = unit ? (double)acc->la2_u : acc->la2_d;
     unsigned long long *dst = pp.st[t]->vals[par][pp.rank];

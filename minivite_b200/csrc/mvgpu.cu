@@ -3,12 +3,14 @@
 // Replaces miniVite's distLouvainMethod (reference dspl.hpp:1280-1441) for one rank == one GPU:
 //   setup      format conversion + ghost discovery + init   (dspl.hpp:1106-1272, 151-172)
 //   iteration  scan kernel -> [ghost exchange, barrier] -> fold kernel -> [all-reduce] -> host test
-// Multi-GPU: vertex-range shards; the per-iteration ghost vertex->community map moves as a grouped
-// ncclSend/ncclRecv all-to-all-v with run-constant counts straight into the ghost tail of the
-// community array; Comm{size,degree} of remotely owned communities is read, and their deltas are
-// pushed, directly in the owner's HBM over NVLink (peer pointers obtained through CUDA IPC), which
-// removes the reference's request/reply and delta-push message rounds (dspl.hpp:719-929, 1022-1102);
-// modularity is one ncclAllReduce of two doubles (dspl.hpp:441).
+// Multi-GPU: vertex-range shards, one rank per GPU.  Comm{size,degree} of remotely owned communities is read, and
+// their deltas are pushed, directly in the owner's HBM over NVLink (peer pointers obtained through CUDA IPC), which
+// removes the reference's request/reply and delta-push message rounds (dspl.hpp:719-929, 1022-1102).  The
+// per-iteration ghost vertex->community map and the modularity reduction (dspl.hpp:559-646, 441) run, by default
+// (comm_mode 1), as this library's own kernels over the same peer memory: k_push_ghosts stores every send segment
+// straight into the ghost tail of the peer's community array, k_p2p_barrier / k_p2p_allreduce are flag-based
+// collectives.  comm_mode 0 keeps them as one grouped ncclSend/ncclRecv all-to-all-v with run-constant counts plus
+// one ncclAllReduce of two doubles.  The setup exchanges (ghost lists, counts, IPC handles) always use NCCL.
 #include <cuda_runtime.h>
 #include <unistd.h>
 
