@@ -156,3 +156,21 @@ def test_cli_multi_gpu(tmp_path, golden):
     assert p.returncode == 0, p.stderr[-2000:]
     it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
     assert len(it) == case["iters"] and it[-1][3] == case["trace"][-1]["chash"]
+
+
+def test_full_size_config4_eight_gpus(tmp_path):
+    """BASELINE.json configs[3]: RGG -n 67108864 sharded across 8 GPUs.  Golden trace: the unmodified reference on 8
+    ranks reading the same graph (tests/golden/golden_full_67108864_p8.json, tools/make_fullsize_golden.py 67108864 8)."""
+    if ngpus() < 8:
+        pytest.skip("needs 8 GPUs")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full_67108864_p8.json")))
+    exe = os.path.join(ROOT, "bin", "miniVite_b200")
+    for extra in ([], ["-D"]):                    # graph built on the host / on the GPUs
+        p = subprocess.run([exe, "-g", "8", "-n", str(gold["nv"]), "-T"] + extra, capture_output=True, text=True, timeout=1500)
+        assert p.returncode == 0, p.stderr[-2000:]
+        it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
+        assert len(it) == gold["iters"]
+        for (k, m, mv, h), g in zip(it, gold["trace"]):
+            assert float(m) == float(g["modularity"]) and int(mv) == g["moved"] and h == g["chash"], k
+        m = re.search(r"Modularity, #Iterations: (\S+), (\d+)", p.stdout)
+        assert m and int(m.group(2)) == gold["iters"]

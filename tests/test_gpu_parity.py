@@ -266,3 +266,27 @@ def test_full_size_config3_random_edges(gpu):
         assert float(t["modularity"]) == float(g["modularity"]) and int(t["moved"]) == g["moved"]
         assert int(t["chash"]) == int(g["chash"], 16)
     assert "%016x" % O.comm_hash(0, res["comm"]) == gold["final_chash"]
+
+
+def test_full_size_config4_on_one_gpu():
+    """BASELINE.json configs[3] (RGG -n 67108864 built on 8 strips) also fits ONE B200: unit-weight results are
+    partition invariant, so a single GPU must reproduce the 8-rank reference trace
+    (tests/golden/golden_full_67108864_p8.json).  12.4 GB of host graph: opt-in with MV_BIG_TESTS=1."""
+    import json
+    import os
+    if os.environ.get("MV_BIG_TESTS") != "1":
+        pytest.skip("set MV_BIG_TESTS=1 (12 GB host graph, about a minute)")
+    from minivite_b200 import gpu as G
+    from minivite_b200 import hostgraph as hg
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_full_67108864_p8.json")))
+    ss = hg.generate_rgg(gold["nv"], gold["strips"])
+    offs = np.cumsum([0] + [s.lne for s in ss.shards[:-1]])
+    rowptr = np.concatenate([[0]] + [s.rowptr[1:] + off for s, off in zip(ss.shards, offs)]).astype(np.int64)
+    edges = np.concatenate([s.edges for s in ss.shards])
+    ss.close()
+    assert len(edges) == gold["ne"]
+    res = run_single(G, np.array([0, gold["nv"]], np.int64), rowptr, edges, gold["nv"])
+    assert res["iters"] == gold["iters"] and repr(res["modularity"]) == repr(float(gold["modularity"]))
+    for t, g in zip(res["trace"], gold["trace"]):
+        assert float(t["modularity"]) == float(g["modularity"]) and int(t["moved"]) == g["moved"]
+        assert int(t["chash"]) == int(g["chash"], 16)
