@@ -30,7 +30,32 @@ struct GpuRankContext {
   std::exit(99);
 }
 
-// The 8 scratch parameters (ssz ... rvdata) are caller-owned out-params that only the reference's
+// Developer knobs, not part of the reference's surface: MVGPU_OPTIONS="name=value,name=value" is handed to
+// mvgpu_set_option (unknown names abort), MVGPU_REPEAT=n runs the phase n times (same result; timings of the last,
+// warm, run are reported).
+inline void mv_apply_env_options(mvgpu_ctx *ctx) {
+  const char *e = std::getenv("MVGPU_OPTIONS");
+  if (!e) return;
+  std::string s(e);
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t end = s.find(',', pos);
+    if (end == std::string::npos) end = s.size();
+    const std::string kv = s.substr(pos, end - pos);
+    pos = end + 1;
+    if (kv.empty()) continue;
+    const size_t eq = kv.find('=');
+    if (eq == std::string::npos) { std::fprintf(stderr, "[miniVite_b200] MVGPU_OPTIONS: missing '=' in %s\n", kv.c_str()); std::exit(99); }
+    if (mvgpu_set_option(ctx, kv.substr(0, eq).c_str(), std::atoll(kv.c_str() + eq + 1))) mv_abort("MVGPU_OPTIONS");
+  }
+}
+inline int mv_env_repeat() {
+  const char *e = std::getenv("MVGPU_REPEAT");
+  const int n = e ? std::atoi(e) : 1;
+  return n < 1 ? 1 : n;
+}
+
+// The 6 scratch parameters (ssz ... rvdata) are caller-owned out-params that only the reference's
 // exchangeVertexReqs filled (dspl.hpp:1106-1272); the ghost lists now live in device memory, so they
 // are left empty.
 inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph &dg, size_t &ssz, size_t &rsz,
@@ -44,11 +69,13 @@ inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph
   if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
   if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
   if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
+  mv_apply_env_options(ctx);
   if (mvgpu_upload_shard(ctx, dg.get_nv(), dg.parts().data(), dg.get_lnv(), dg.get_lne(), dg.edge_indices_.data(),
                          dg.edge_list_.data()))
     mv_abort("mvgpu_upload_shard");
   double mod = 0.0;
-  if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
+  for (int rep = mv_env_repeat(); rep > 0; rep--)
+    if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
   mvgpu_get_timings(ctx, &rc.timings);
   if (rc.trace) {
     int n = 0;
@@ -75,6 +102,7 @@ inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, 
   if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
   if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
   if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
+  mv_apply_env_options(ctx);
   const auto t0 = std::chrono::steady_clock::now();
   int64_t lne64 = 0;
   if (mvgpu_generate_rgg_shard(ctx, nv, unitEdgeWeight ? 1 : 0, &lne64)) mv_abort("mvgpu_generate_rgg_shard");
@@ -82,7 +110,8 @@ inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, 
   lne = lne64;
   before_louvain();
   double mod = 0.0;
-  if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
+  for (int rep = mv_env_repeat(); rep > 0; rep--)
+    if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
   mvgpu_get_timings(ctx, &rc.timings);
   if (rc.trace) {
     int n = 0;

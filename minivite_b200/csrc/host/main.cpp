@@ -276,6 +276,9 @@ int main(int argc, char *argv[]) {
     std::cout << "GPU Louvain phase (in s), H2D upload (in s): " << avgd << ", " << rc.timings.h2d_s << std::endl;
     std::cout << "Edges/s (ne*iters/t), s/iter: " << (double)ne_rep * iters / avgd << ", " << avgd / iters << std::endl;
     std::cout << "-------------------------------------------------------" << std::endl;
+    fprintf(stderr, "TIMINGS_MS total=%.3f setup=%.3f reorder=%.3f scan=%.3f fold=%.3f exchange=%.3f launches=%d reordered=%d\n",
+            rc.timings.total_s * 1e3, rc.timings.setup_s * 1e3, rc.timings.reorder_s * 1e3, rc.timings.scan_s * 1e3,
+            rc.timings.fold_s * 1e3, rc.timings.exchange_s * 1e3, (int)rc.timings.kernel_launches, (int)rc.timings.reordered);
     fprintf(stderr, "RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d threads=0\n", currMod, iters, avgd,
             (long)nv_rep, (long)ne_rep, nprocs);
   }

@@ -1088,11 +1088,8 @@ __global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *
 constexpr unsigned int kBfsRegionBits = 22;
 constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
 
-// `fanout` > 0 (option bfs_fanout, experimental) expands only the first `fanout` edges of a frontier vertex: the
-// random key[] probes are what the search costs, and a few edges per vertex already connect almost everything;
-// k_bfs_adopt then attaches the vertices no sampled edge pointed at to their best reached neighbour.
 __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
-                                               int region_stride, int max_levels, unsigned int *level_flags, int fanout) {
+                                               int region_stride, int max_levels, unsigned int *level_flags) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -1117,9 +1114,7 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
         const int b = __ffs(m) - 1;
         m &= m - 1;
         const unsigned int kb = __shfl_sync(0xffffffffu, k, b);
-        const uint32_t e0 = __shfl_sync(0xffffffffu, r0, b);
-        uint32_t e1 = __shfl_sync(0xffffffffu, r1, b);
-        if (fanout > 0 && e1 - e0 > (uint32_t)fanout) e1 = e0 + (uint32_t)fanout;
+        const uint32_t e0 = __shfl_sync(0xffffffffu, r0, b), e1 = __shfl_sync(0xffffffffu, r1, b);
         const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (kb & ((1u << kBfsRegionBits) - 1));
         for (uint32_t e = e0 + lane; e < e1; e += 32) {
           const int w = tails[e];
@@ -1134,27 +1129,6 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
 }
 
 // sort key: region major, level minor; unreached vertices (other components) last, in id order
-// bfs_fanout only: a vertex the sampled search did not reach takes the smallest key among ALL its neighbours, one
-// level further out (key_out is a separate array, so the result does not depend on thread order)
-__global__ void __launch_bounds__(256) k_bfs_adopt(int lnv, const uint32_t *rowptr, const int32_t *tails, const uint32_t *key,
-                                                   uint32_t *key_out) {
-  for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
-    unsigned int k = key[v];
-    if (k == kBfsUnreached) {
-      unsigned int best = kBfsUnreached;
-      for (uint32_t e = rowptr[v]; e < rowptr[v + 1]; e++) {
-        const int w = tails[e];
-        if (w < lnv) best = min(best, key[w]);
-      }
-      if (best != kBfsUnreached) {
-        const unsigned int level = min((best >> kBfsRegionBits) + 1u, 1023u);
-        k = (level << kBfsRegionBits) | (best & ((1u << kBfsRegionBits) - 1));
-      }
-    }
-    key_out[v] = k;
-  }
-}
-
 __global__ void __launch_bounds__(256) k_bfs_sortkeys(int lnv, const uint32_t *key, uint32_t *sortkey, int32_t *ids) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
     const unsigned int k = key[v];

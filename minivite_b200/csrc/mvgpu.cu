@@ -162,7 +162,7 @@ struct mvgpu_ctx {
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_bfs_fanout = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -552,17 +552,9 @@ int setup_run(mvgpu_ctx *c) {
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
         const uint32_t *rp = src_rowptr; const int32_t *tl = src_tails; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        int fanout = c->opt_bfs_fanout;
-        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf, &fanout};
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
-        const uint32_t *keys = c->bfs_key.p;
-        if (fanout > 0) {
-          TRY(c->bfs_visited.ensure(lnv));
-          k_bfs_adopt<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, src_rowptr, src_tails, c->bfs_key.p, c->bfs_visited.p);
-          c->tm.kernel_launches++;
-          keys = c->bfs_visited.p;
-        }
-        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, keys, c->sortkey.p, c->ids.p);
+        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s);
         TRY(c->cub_tmp.ensure(tb));
@@ -1202,7 +1194,6 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;
   else if (n == "compact_upload") c->opt_compact_upload = (int)value;
   else if (n == "host_threads") c->opt_host_threads = (int)value;
-  else if (n == "bfs_fanout") { if (value < 0) return fail("bfs_fanout < 0"); c->opt_bfs_fanout = (int)value; }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;
