@@ -82,3 +82,30 @@ def test_balanced_reader_matches_reference_bins(golden, tmp_path):
     # vertex-balanced reader for comparison
     sh = hg.read_graph(path, 1, 4, balanced=False).shards[0]
     assert sh.base == 4096 and sh.lnv == 4096
+
+
+def _fnv1a_words(vec):
+    h = 1469598103934665603
+    for v in vec.tolist():
+        h = ((h ^ (v & 0xFFFFFFFFFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+@pytest.mark.parametrize("name,ncomm,fnv", [("rgg_n16384_p1", 1953, "2788b5ffe2f49136"),
+                                            ("rgg_n65536_p1", 6889, "3cf802502bc50070"),
+                                            ("file_rgg_n524288_s1_p1", 48778, "188df44bd1f5b787")])
+def test_final_assignment_matches_survey_known_answers(golden, name, ncomm, fnv):
+    """number of communities and FNV-1a hash of the final currComm, captured from the unmodified
+    reference in a separate probe session (a pin that does not pass through this repo's own hash or hooks)."""
+    parts, rps, eds, _keep = case_graph(golden[name])
+    res = O.louvain(parts, rps, eds)
+    comm = np.concatenate(res["comm"])
+    assert len(np.unique(comm)) == ncomm
+    assert _fnv1a_words(comm) == fnv
+
+
+def test_rgg_radius_matches_survey_table():
+    from minivite_b200 import hostgraph as hg
+    assert abs(hg.rgg_radius(16384) - 1.249e-2) < 5e-6          # SURVEY.md section 8 config table (graph.hpp:629-631)
+    assert abs(hg.rgg_radius(16777216) - 4.567e-4) < 5e-8
+    assert abs(hg.rgg_radius(67108864, 8) - 2.341e-4) < 5e-8
