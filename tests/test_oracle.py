@@ -18,6 +18,18 @@ def test_golden_file_has_all_kinds(golden):
     assert kinds == {"rgg", "file_rgg", "hand", "file_balanced"}
     assert golden["rgg_n16384_p1"]["modularity"] == "0.75671532450841406"   # SURVEY.md 8(c) known answer
     assert golden["rgg_n16384_p1"]["final_chash"] == "5bf1e47053c42601"
+    # SURVEY.md 8(c), p-strip graphs made by the reference generator on p ranks, and the shard-combinable trace hashes
+    for name, ne, iters, mod, ch in (("rgg_n16384_p2", 131178, 16, "0.77055664274182301", "80ae93c9830e0ce7"),
+                                     ("rgg_n16384_p4", 129262, 14, "0.76142299956738535", "cd26d5284d897ead"),
+                                     ("rgg_n16384_p8", 130920, 20, "0.74390133494621125", "2a8ec661d39110ca"),
+                                     ("rgg_n65536_p1", 564602, 18, "0.76023592129323059", None)):
+        c = golden[name]
+        assert (c["ne"], c["iters"], c["modularity"]) == (ne, iters, mod), name
+        assert ch is None or c["final_chash"] == ch, name
+    tr = golden["rgg_n16384_p1"]["trace"]
+    assert (tr[0]["modularity"], tr[0]["moved"], tr[0]["chash"]) == ("0.00017722880436126689", 9302, "6e0f20678d8ceb80")
+    assert (tr[1]["modularity"], tr[1]["moved"], tr[1]["chash"]) == ("0.2003383411625265", 9028, "85e25e5c7dba5389")
+    assert (tr[13]["moved"], tr[13]["chash"]) == (738, "e9f74809e145f6bd")          # the rejected 14th iteration
     # `miniVite -n 524288` on 1 and 8 ranks (graph files written by our byte-identical generator)
     c1, c8 = golden["file_rgg_n524288_s1_p1"], golden["file_rgg_n524288_s8_p8"]
     assert (c1["ne"], c1["iters"], c1["modularity"]) == (4997382, 20, "0.75810023251607561")
