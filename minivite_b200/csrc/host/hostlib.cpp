@@ -37,6 +37,17 @@ int mvh_rgg_generate(int64_t nv, int nprocs, int r_begin, int r_end, int is_lcg,
   });
 }
 
+// utils.hpp:91-98 and the coordinates rank r of the reference draws (graph.hpp:680-700 / LCG utils.hpp:118-303)
+int64_t mvh_reseeder(unsigned initseed) { return (int64_t)mvhost::reseeder(initseed); }
+int mvh_rgg_points(int64_t nv, int nprocs, int r, int is_lcg, int64_t count, double *x, double *y) {
+  return guarded([&] {
+    mvhost::GenerateRGG gr(nv, nprocs);
+    std::vector<GraphWeight> X, Y;
+    gr.strip_points(r, is_lcg != 0, X, Y);
+    for (int64_t i = 0; i < count && i < (int64_t)X.size(); i++) { x[i] = X[i]; y[i] = Y[i]; }
+  });
+}
+
 double mvh_rgg_radius(int64_t nv, int nprocs) {
   try { return mvhost::GenerateRGG(nv, nprocs).get_d(); } catch (...) { return -1.0; }
 }

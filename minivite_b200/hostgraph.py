@@ -35,6 +35,10 @@ def lib():
         L.mvh_graph_write.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.mvh_graph_free.argtypes = [ctypes.c_void_p]
         L.mvh_set_num_threads.argtypes = [ctypes.c_int]
+        L.mvh_reseeder.restype = ctypes.c_int64
+        L.mvh_reseeder.argtypes = [ctypes.c_uint]
+        L.mvh_rgg_points.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                     ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -110,6 +114,19 @@ def generate_rgg(nv, nprocs=1, r_begin=0, r_end=-1, lcg=False, unit_weight=True,
     _check(lib().mvh_rgg_generate(nv, nprocs, r_begin, r_end, int(lcg), int(unit_weight),
                                   float(random_edge_percent), ctypes.byref(h)))
     return ShardSet(h.value)
+
+
+def reseeder(initseed=1):
+    """The reference's seed helper (utils.hpp:91-98)."""
+    return int(lib().mvh_reseeder(initseed))
+
+
+def rgg_points(nv, nprocs=1, rank=0, count=None, lcg=False):
+    """First `count` coordinates (X, Y) rank `rank` of `miniVite -n nv` on nprocs ranks draws (graph.hpp:680-700)."""
+    n = nv // nprocs if count is None else min(count, nv // nprocs)
+    x, y = np.zeros(n, np.float64), np.zeros(n, np.float64)
+    _check(lib().mvh_rgg_points(nv, nprocs, rank, int(lcg), n, x.ctypes.data, y.ctypes.data))
+    return x, y
 
 
 def rgg_radius(nv, nprocs=1):

@@ -55,3 +55,22 @@ def test_graph_is_symmetric_and_sorted():
     for v in range(0, sh.lnv, 97):
         seg = dst[sh.rowptr[v]:sh.rowptr[v + 1]]
         assert np.all(np.diff(seg) >= 0)
+
+
+def test_generator_rng_known_answers():
+    """SURVEY.md 8(c) RNG known answers of the reference generator (utils.hpp:91-98, graph.hpp:682-700): the seed,
+    the minstd_rand0 stream behind std::default_random_engine and the first coordinates at 1 rank."""
+    seed = hg.reseeder(1)
+    assert seed == 1967017404
+    raw, x = [], seed
+    for _ in range(4):
+        x = x * 16807 % 2147483647
+        raw.append(x)
+    assert raw == [1298247110, 1205324250, 671427599, 1804575055]
+    X, Y = hg.rgg_points(16384, 1, 0, 2)
+    assert repr(float(X[0])) == "0.5612728422168126" and float(X[0]) == 0.56127284221681262
+    assert float(Y[0]) == 0.84032074361727549 and float(X[1]) == 0.27303256924115216
+    # every strip restarts from the same seed: same X, Y shifted into the strip (graph.hpp:697-700)
+    X2, Y2 = hg.rgg_points(16384, 4, 3, 2)
+    X0, Y0 = hg.rgg_points(16384, 4, 0, 2)
+    assert np.array_equal(X2, X0) and np.all((Y2 >= 0.75) & (Y2 < 1.0)) and np.all(Y0 < 0.25)
