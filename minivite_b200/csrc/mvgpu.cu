@@ -162,7 +162,7 @@ struct mvgpu_ctx {
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_degree_sort = 0;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -181,6 +181,34 @@ struct mvgpu_ctx {
 };
 
 namespace {
+
+// Layout refinement on top of the BFS order (option "degree_sort" = window size, experimental, off by default):
+// inside every window of W consecutive positions the vertices are put in ascending degree order (stable), so the 32
+// lanes of a scan warp -- which walk their neighbour lists in lock step, trip count = longest list -- get lists of
+// similar length.  The window stays inside a few BFS regions, so gather locality is kept.  Layout only.
+template <int ITEMS>
+__global__ void __launch_bounds__(256) k_window_degree_sort(int lnv, const uint32_t *rowptr, int32_t *perm) {
+  using Sort = cub::BlockRadixSort<unsigned int, 256, ITEMS, int>;
+  __shared__ typename Sort::TempStorage tmp;
+  const int w0 = blockIdx.x * 256 * ITEMS;
+  unsigned int key[ITEMS];
+  int val[ITEMS];
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const int pos = w0 + threadIdx.x * ITEMS + k;
+    if (pos < lnv) {
+      const int v = perm[pos];
+      val[k] = v;
+      key[k] = min(rowptr[v + 1] - rowptr[v], 126u);
+    } else { val[k] = -1; key[k] = 127u; }          // padding sorts behind every real vertex
+  }
+  Sort(tmp).Sort(key, val, 0, 7);
+#pragma unroll
+  for (int k = 0; k < ITEMS; k++) {
+    const int pos = w0 + threadIdx.x * ITEMS + k;
+    if (pos < lnv) perm[pos] = val[k];
+  }
+}
 
 int grid_for(long long n, int threads, int num_sms, int per_sm = 8) {
   long long b = (n + threads - 1) / threads;
@@ -561,6 +589,14 @@ int setup_run(mvgpu_ctx *c) {
         tb = c->cub_tmp.cap;
         CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s));
         c->tm.kernel_launches += 3;
+        if (c->opt_degree_sort) {
+          const int items = c->opt_degree_sort / 256;
+          const int nb = (int)((lnv + c->opt_degree_sort - 1) / c->opt_degree_sort);
+          if (items == 2) k_window_degree_sort<2><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
+          else if (items == 4) k_window_degree_sort<4><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
+          else k_window_degree_sort<8><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
+          c->tm.kernel_launches++;
+        }
       } else {
         // another rank renumbers, this one keeps its order: identity permutation, labels still required
         k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->perm.p);
@@ -1194,6 +1230,10 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;
   else if (n == "compact_upload") c->opt_compact_upload = (int)value;
   else if (n == "host_threads") c->opt_host_threads = (int)value;
+  else if (n == "degree_sort") {
+    if (value != 0 && value != 512 && value != 1024 && value != 2048) return fail("degree_sort must be 0, 512, 1024 or 2048");
+    c->opt_degree_sort = (int)value;
+  }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;

@@ -215,7 +215,8 @@ def test_locality_renumbering_keeps_results(gpu, golden):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
         for opts in ({"reorder": 1, "region_size": 64}, {"reorder": 1, "region_size": 4096, "scan_variant": 0},
-                     {"reorder": 1, "region_size": 32, "force_heavy_deg": 3}):
+                     {"reorder": 1, "region_size": 32, "force_heavy_deg": 3},
+                     {"reorder": 1, "region_size": 64, "degree_sort": 512}):
             res = run_single(gpu, parts, rowptr, edges, nv, **opts)
             assert res["timings"]["reordered"] == 1, (name, opts)
             assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
