@@ -1025,6 +1025,50 @@ __global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int
 }
 
 // distSumVertexDegree + distInitComm + self-loop weights (dspl.hpp:82-107, 132-149, 247-248/285)
+// Unit-weight fold, four community slots per thread and iteration (option fold_variant=1, experimental): same
+// arithmetic as k_fold<true>, 16-byte loads so that more bytes are in flight per thread.
+__device__ __forceinline__ uint32_t fold_apply_unit(uint32_t dg, unsigned long long u, int32_t *csize_i) {
+  const int ddeg = (int)(uint32_t)u;
+  const int dsize = (int)(((long long)u - (long long)ddeg) >> 32);
+  if (dsize) *csize_i += dsize;
+  return dg + (uint32_t)ddeg;
+}
+__global__ void __launch_bounds__(256) k_fold_unit4(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, Acc *acc) {
+  unsigned long long a2u = 0;
+  const int n4 = lnv >> 2;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
+    uint4 dg = reinterpret_cast<const uint4 *>(cdeg)[q];
+    const ulonglong2 ua = reinterpret_cast<const ulonglong2 *>(upd)[2 * q], ub = reinterpret_cast<const ulonglong2 *>(upd)[2 * q + 1];
+    if (ua.x | ua.y | ub.x | ub.y) {
+      const int i = 4 * q;
+      if (ua.x) dg.x = fold_apply_unit(dg.x, ua.x, csize + i);
+      if (ua.y) dg.y = fold_apply_unit(dg.y, ua.y, csize + i + 1);
+      if (ub.x) dg.z = fold_apply_unit(dg.z, ub.x, csize + i + 2);
+      if (ub.y) dg.w = fold_apply_unit(dg.w, ub.y, csize + i + 3);
+      reinterpret_cast<uint4 *>(cdeg)[q] = dg;
+      const ulonglong2 z = make_ulonglong2(0ULL, 0ULL);
+      if (ua.x | ua.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q] = z;
+      if (ub.x | ub.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q + 1] = z;
+    }
+    a2u += (unsigned long long)dg.x * dg.x + (unsigned long long)dg.y * dg.y + (unsigned long long)dg.z * dg.z +
+           (unsigned long long)dg.w * dg.w;
+  }
+  if (blockIdx.x == 0) {                          // the up to three slots behind the last full group
+    const int i = 4 * n4 + (int)threadIdx.x;
+    if (i < lnv) {
+      uint32_t dg = cdeg[i];
+      const unsigned long long u = upd[i];
+      if (u) { dg = fold_apply_unit(dg, u, csize + i); cdeg[i] = dg; upd[i] = 0; }
+      a2u += (unsigned long long)dg * dg;
+    }
+  }
+  __shared__ unsigned long long su[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long s = warp_sum(a2u);
+  if (lane == 0) su[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < 8; w++) t += su[w]; atomicAdd(&acc->la2_u, t); }
+}
 template <bool UNIT>
 __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, const uint32_t *rowptr, const int32_t *tails,
                                                      const double *weights, int32_t *cur, uint32_t *cdeg, int32_t *csize,

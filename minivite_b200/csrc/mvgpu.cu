@@ -162,7 +162,7 @@ struct mvgpu_ctx {
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_degree_sort = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_degree_sort = 0, opt_fold_variant = 0;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -778,7 +778,9 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       }
     }
     CK(cudaEventRecord(e2, s));
-    if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, acc);
+    if (c->unit && c->opt_fold_variant == 1)
+      k_fold_unit4<<<grid_for((c->lnv >> 2) + 1, 256, c->num_sms, 8), 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, acc);
+    else if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, acc);
     else k_fold<false><<<fold_grid, 256, 0, s>>>((int)c->lnv, nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
     c->tm.kernel_launches++;
     CK(cudaEventRecord(e3, s));
@@ -1230,6 +1232,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;
   else if (n == "compact_upload") c->opt_compact_upload = (int)value;
   else if (n == "host_threads") c->opt_host_threads = (int)value;
+  else if (n == "fold_variant") c->opt_fold_variant = (int)value;
   else if (n == "degree_sort") {
     if (value != 0 && value != 512 && value != 1024 && value != 2048) return fail("degree_sort must be 0, 512, 1024 or 2048");
     c->opt_degree_sort = (int)value;
