@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--nv-per-gpu", type=int, default=NV_PER_GPU, help="dev knob; the benchmark config is the default")
     ap.add_argument("--cpu-sample-nv", type=int, default=2097152)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compact-upload", type=int, default=0, metavar="THREADS",
+                    help="dev knob for the e2e leg: narrow unit-weight shards to 4-byte tails with THREADS host threads "
+                         "before the H2D copy (library option compact_upload; default off)")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
 
@@ -296,6 +299,9 @@ def main():
     info = ctx.shard_info()
 
     # ---- e2e: host arrays -> H2D -> Louvain -> assignment D2H, through the public API
+    if args.compact_upload > 0:
+        ctx.set_option("compact_upload", 1)
+        ctx.set_option("host_threads", args.compact_upload)
     e2e_t = []
     h_comm = torch.empty(sh.lnv, dtype=torch.int64).pin_memory().numpy()      # the user's (pinned) result buffer
     for k in range(args.warmup + args.steps):
@@ -346,6 +352,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "nv": nv_total, "ne": ne_total, "iterations": iters,
                        "modularity": mod, "s_per_iter": t_dev / iters, "l2": "inputs (3 GB/GPU) larger than L2; no flush",
+                       "compact_upload_threads": args.compact_upload,
                        "unit_weight_path": bool(tm_last["unit_weight"]), "nghost": info["nghost"],
                        "arithmetic": "modularity gains in fp64 with the reference's rounding sequence; ids int32 on the device "
                                      "(int64 at the boundary); unit-weight degrees as exact integers",

@@ -30,6 +30,10 @@
 #include "nccl_dyn.h"
 #include "rgg_gpu.cuh"
 
+// host-only helper of the compact upload (narrow.cpp): 16-byte edge records -> 4-byte tails + validation
+extern "C" void mv_narrow_edges(const void *edge_records, long long n, long long nv, long long base, long long bound,
+                                int32_t *dst, long long *nremote, int *bad);
+
 namespace {
 
 thread_local std::string g_err;
@@ -975,16 +979,9 @@ static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const vo
       const long long i = next.fetch_add(1);
       if (i >= nchunks || bad.load(std::memory_order_relaxed)) break;
       const long long off = i * CH, n = std::min<long long>(CH, lne - off);
-      const Edge16 *src = E + off;
-      int32_t *dst = stage + off;
       long long nrem = 0;
       int b = 0;
-      for (long long e = 0; e < n; e++) {
-        const long long t = src[e].tail;
-        b |= (src[e].weight != 1.0) | (t < 0) | (t >= nv_global);
-        dst[e] = (int32_t)t;
-        nrem += (t < base) | (t >= bound);
-      }
+      mv_narrow_edges(E + off, n, nv_global, base, bound, stage + off, &nrem, &b);
       if (b) bad.store(1);
       nremote.fetch_add(nrem);
       done[i].store(1, std::memory_order_release);

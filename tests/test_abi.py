@@ -46,3 +46,42 @@ def test_product_does_not_import_oracle():
                     code = line.split("//")[0]
                     for pat in pats:
                         assert not re.search(pat, code), (os.path.join(dp, f), line.strip())
+
+
+def test_compact_upload_host_pass():
+    """The host half of compact_upload (narrow.cpp, AVX2 or scalar body): 16-byte {tail, weight} records -> int32 tails,
+    with the same validation as the device pass and the count of non-owned tails.  Pure host code inside libmvgpu.so."""
+    import ctypes
+    import numpy as np
+    from minivite_b200 import gpu as G
+    from minivite_b200 import hostgraph as hg
+    L = G.lib()
+    fn = L.mv_narrow_edges
+    fn.restype = None
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                   ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)]
+
+    def run(edges, nv, base, bound):
+        out = np.full(len(edges) + 4, -7, np.int32)
+        nrem, bad = ctypes.c_longlong(0), ctypes.c_int(0)
+        fn(edges.ctypes.data, len(edges), nv, base, bound, out.ctypes.data, ctypes.byref(nrem), ctypes.byref(bad))
+        assert np.all(out[len(edges):] == -7)                      # nothing written past the end
+        return out[:len(edges)], nrem.value, bad.value
+
+    rng = np.random.RandomState(3)
+    for n in (0, 1, 3, 4, 5, 63, 64, 1001):
+        e = np.zeros(n, hg.EDGE_DTYPE)
+        e["tail"] = rng.randint(0, 5000, size=n)
+        e["weight"] = 1.0
+        out, nrem, bad = run(e, 5000, 1000, 3000)
+        assert bad == 0 and np.array_equal(out, e["tail"].astype(np.int32))
+        assert nrem == int(np.sum((e["tail"] < 1000) | (e["tail"] >= 3000)))
+    e = np.zeros(37, hg.EDGE_DTYPE)
+    e["tail"] = np.arange(37)
+    e["weight"] = 1.0
+    for pos in (0, 5, 35, 36):                                      # vector body and scalar tail
+        for field, val in (("weight", 0.5), ("weight", float("nan")), ("tail", -1), ("tail", 37)):
+            f = e.copy()
+            f[field][pos] = val
+            assert run(f, 37, 0, 37)[2] == 1, (pos, field, val)
+    assert run(e, 37, 0, 37)[1:] == (0, 0)
