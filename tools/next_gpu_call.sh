@@ -15,6 +15,14 @@ mkdir -p gpurun_out
     echo "opts=$o"
     MVGPU_REPEAT=3 MVGPU_OPTIONS=$o timeout 300 bin/miniVite_b200 -n 16777216 -p 2 2>&1 | grep -E "TIMINGS|RESULT|rror"
   done
+  echo "== compile-time variants built with tools/build_variant.sh (if any)"
+  for b in variants/*/bin/miniVite_b200; do
+    [ -x "$b" ] || continue
+    for o in "" degree_sort=1024; do
+      echo "variant=$b opts=$o"
+      MVGPU_REPEAT=3 MVGPU_OPTIONS=$o timeout 120 $b -n 16777216 -D 2>&1 | grep -E "TIMINGS|RESULT|rror"
+    done
+  done
 } > gpurun_out/next_cli.log 2>&1
 # Part 2: parity of everything new (tests added after the last GPU run of round 1)
 timeout 900 python -m pytest tests -q -m gpu -k "survey or experimental or renumbering or unit_weight_cases" > gpurun_out/next_pytest.log 2>&1
