@@ -138,7 +138,6 @@ __device__ __forceinline__ void st_pol(int32_t *p, int v, unsigned long long pol
   asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
 
-struct ScanParams;
 template <bool MULTI>
 __device__ __forceinline__ void locate_impl(const PeerTable &pt, long long base, int lnv, int y, int &owner, long long &idx) {
   if (!MULTI) { owner = 0; idx = (long long)y - base; return; }
@@ -252,8 +251,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // The neighbour-scan kernel: distExecuteLouvainIteration + distBuildLocalMapCounter +
 // distGetMaxIndex (dspl.hpp:276-405, 230-274, 174-228) for every vertex of the shard.
 //
-// One CTA owns a tile of 256 consecutive vertices; their CSR edges are one contiguous range.
-//   phase A (edge-parallel, all 256 lanes busy, coalesced): stream the int32 tails of the tile,
+// One CTA owns a tile of kTileV (128) consecutive vertices; their CSR edges are one contiguous range.
+//   phase A (edge-parallel, all lanes busy, coalesced): stream the int32 tails of the tile,
 //           gather cur[tail] (the only random access per edge; 4 B from an L2-resident array) and
 //           stage the neighbour communities (and weights) in shared memory;
 //   phase B (vertex-parallel): each thread reduces its vertex's staged segment to
