@@ -107,7 +107,7 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * streamed arrays; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
  * vertices per BFS region of the renumbering, default 512), "degree_sort" (experimental layout refinement of the
- * renumbering: vertices ordered by degree inside windows of 512 / 1024 / 2048 positions; 0 (default) = off), "fold_variant" (experimental: 1 = unit-weight fold
+ * renumbering: vertices ordered by degree inside windows of 256 / 512 / 1024 / 2048 positions; 0 (default) = off), "fold_variant" (experimental: 1 = unit-weight fold
  * with 16-byte accesses; 0 (default)), "comm_mode" (multi-GPU per-iteration exchanges: 1 = stores /
  * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "compact_upload" (1:
  * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 0 (default) = the 16-byte

@@ -596,7 +596,8 @@ int setup_run(mvgpu_ctx *c) {
         if (c->opt_degree_sort) {
           const int items = c->opt_degree_sort / 256;
           const int nb = (int)((lnv + c->opt_degree_sort - 1) / c->opt_degree_sort);
-          if (items == 2) k_window_degree_sort<2><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
+          if (items == 1) k_window_degree_sort<1><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
+          else if (items == 2) k_window_degree_sort<2><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
           else if (items == 4) k_window_degree_sort<4><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
           else k_window_degree_sort<8><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
           c->tm.kernel_launches++;
@@ -1231,7 +1232,8 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "host_threads") c->opt_host_threads = (int)value;
   else if (n == "fold_variant") c->opt_fold_variant = (int)value;
   else if (n == "degree_sort") {
-    if (value != 0 && value != 512 && value != 1024 && value != 2048) return fail("degree_sort must be 0, 512, 1024 or 2048");
+    if (value != 0 && value != 256 && value != 512 && value != 1024 && value != 2048)
+      return fail("degree_sort must be 0, 256, 512, 1024 or 2048");
     c->opt_degree_sort = (int)value;
   }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }

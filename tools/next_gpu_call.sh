@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 {
   echo "== config 2 (-n 16777216), 3 warm repeats, options one at a time"
-  for o in "" degree_sort=512 degree_sort=1024 degree_sort=2048 fold_variant=1 "degree_sort=1024,fold_variant=1" region_size=256 region_size=1024; do
+  for o in "" degree_sort=256 degree_sort=512 degree_sort=1024 degree_sort=2048 fold_variant=1 "degree_sort=1024,fold_variant=1" region_size=256 region_size=1024; do
     echo "opts=$o"
     MVGPU_REPEAT=3 MVGPU_OPTIONS=$o timeout 120 bin/miniVite_b200 -n 16777216 -D 2>&1 | grep -E "TIMINGS|RESULT|rror"
   done
