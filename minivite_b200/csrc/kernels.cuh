@@ -119,16 +119,6 @@ __device__ __forceinline__ unsigned long long make_policy(int kind) {   // 0 nor
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ int ld_pol(const int32_t *p, unsigned long long pol) {
-  int v;
-  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ uint32_t ld_pol(const uint32_t *p, unsigned long long pol) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
 __device__ __forceinline__ int ld_pol_stream(const int32_t *p, unsigned long long pol) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -447,85 +437,6 @@ template <bool MULTI>
 __device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
   atomicAdd(at_upd<MULTI>(p, best), pack_delta(1, (long long)d));
   atomicAdd(at_upd<MULTI>(p, cc), pack_delta(-1, -(long long)d));
-}
-
-// generic in-place reduction of one vertex's staged segment (any degree <= kECap), unit weights
-template <bool MULTI>
-__device__ __forceinline__ int slow_vertex_unit(const ScanParams &p, int32_t *s_comm, int32_t *s_cnt, int o0, int d, int v,
-                                                int cc, unsigned long long &acc_le) {
-  int nd = 0, cnt0 = 0;
-  for (int k = 0; k < d; k++) {
-    const int ck = s_comm[o0 + k];
-    if (ck == cc) { cnt0++; continue; }
-    if (ck < 0) continue;
-    int c = 1;
-    for (int j = k + 1; j < d; j++)
-      if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
-    s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
-  }
-  int owner; long long idx;
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
-  const double cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
-  const double vdeg = (double)d;
-  const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
-  const double eix = (double)(cnt0 - sl), ax = __dsub_rn(cc_deg, vdeg);
-  acc_le += (unsigned long long)cnt0;
-  double bg = 0.0;
-  int best = cc, lbest = kNoLabel;
-  for (int m = 0; m < nd; m++) {
-    const int y = s_comm[o0 + m];
-    int yo; long long yi;
-    locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
-    const double ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
-    const double g = gain_of((double)s_cnt[o0 + m], eix, vdeg, ay, ax, p.constant);
-    if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; }
-  }
-  if (label_greater<MULTI>(p, best, lbest, cc)) {                            // dspl.hpp:224-225
-    int bo; long long bi;
-    locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
-    if (__ldg(ptr_csize<MULTI>(p, owner) + idx) == 1 && __ldg(ptr_csize<MULTI>(p, bo) + bi) == 1)
-      best = cc;
-  }
-  return best;
-}
-
-// generic in-place reduction of one vertex's staged segment (any degree <= kECap), weighted
-template <bool MULTI>
-__device__ __forceinline__ int slow_vertex_w(const ScanParams &p, int32_t *s_comm, double *s_w, int o0, int d, int v, int cc,
-                                             double &acc_le, double &vdeg_out) {
-  int nd = 0;
-  double w0 = 0.0;
-  for (int k = 0; k < d; k++) {
-    const int ck = s_comm[o0 + k];
-    if (ck == cc) { w0 += s_w[o0 + k]; continue; }
-    if (ck < 0) continue;
-    double sum = s_w[o0 + k];
-    for (int j = k + 1; j < d; j++)
-      if (s_comm[o0 + j] == ck) { sum += s_w[o0 + j]; s_comm[o0 + j] = -1; }
-    s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
-  }
-  int owner; long long idx;
-  locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
-  const double2 raw = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, owner) + idx));
-  const long long cc_size = __double_as_longlong(raw.x);
-  const double vdeg = __ldg(p.vdeg + v);
-  vdeg_out = vdeg;
-  const double sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
-  const double eix = __dsub_rn(w0, sl), ax = __dsub_rn(raw.y, vdeg);
-  acc_le += w0;
-  double bg = 0.0;
-  int best = cc, lbest = kNoLabel;
-  long long best_size = cc_size;
-  for (int m = 0; m < nd; m++) {
-    const int y = s_comm[o0 + m];
-    int yo; long long yi;
-    locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
-    const double2 ry = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, yo) + yi));
-    const double g = gain_of(s_w[o0 + m], eix, vdeg, ry.y, ax, p.constant);
-    if (better_l<MULTI>(p, g, y, bg, best, lbest)) { bg = g; best = y; best_size = __double_as_longlong(ry.x); }
-  }
-  if (best_size == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lbest, cc)) best = cc;
-  return best;
 }
 
 template <bool MULTI>
