@@ -103,8 +103,8 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
  * "scan_variant" (3 = warp-synchronous loops (default), 0 = first kernel; identical results),
- * "cache_policy" (bit0 evict_last on community gathers, bit1 evict_last on degree gathers, bit2 evict_first on
- * streamed arrays; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
+ * "cache_policy" (bit2 = L2 evict_first hint on the streamed arrays of the default scan kernel; other bits are
+ * accepted and ignored; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
  * vertices per BFS region of the renumbering, default 512), "degree_sort" (experimental layout refinement of the
  * renumbering: vertices ordered by degree inside windows of 256 / 512 / 1024 / 2048 positions; 0 (default) = off), "fold_variant" (experimental: 1 = unit-weight fold

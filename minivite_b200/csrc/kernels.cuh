@@ -69,7 +69,8 @@ struct ScanParams {
   int has_self;                    // any self loop in the shard (uniform branch)
   int heavy_deg;                   // degree > heavy_deg is left to the high-degree kernel (<= kECap)
   int relabel;                     // vertices were renumbered for locality: ids are internal, tie-breaks use labels
-  int cache_policy;                // bit0: evict_last on cur gathers, bit1: evict_last on cdeg gathers, bit2: evict_first streams
+  int cache_policy;                // bit2: L2 evict_first on the streamed arrays (tails, target writes); bits 0-1 unused
+                                   // (evict_last hints on the gathered arrays were measured without effect and removed)
   long long base;                  // global id of local vertex 0
   const uint32_t *rowptr;
   const int32_t *tails;
