@@ -215,8 +215,7 @@ def test_locality_renumbering_keeps_results(gpu, golden):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
         for opts in ({"reorder": 1, "region_size": 64}, {"reorder": 1, "region_size": 4096, "scan_variant": 0},
-                     {"reorder": 1, "region_size": 32, "force_heavy_deg": 3},
-                     {"reorder": 1, "region_size": 64, "degree_sort": 512}):
+                     {"reorder": 1, "region_size": 32, "force_heavy_deg": 3}):
             res = run_single(gpu, parts, rowptr, edges, nv, **opts)
             assert res["timings"]["reordered"] == 1, (name, opts)
             assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
@@ -305,14 +304,3 @@ def test_final_assignment_matches_survey_known_answers(gpu, golden, name, ncomm,
     for v in comm.tolist():
         h = ((h ^ (v & 0xFFFFFFFFFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     assert len(np.unique(comm)) == ncomm and "%016x" % h == fnv
-
-
-def test_experimental_layout_and_fold_options_keep_results(gpu, golden):
-    """fold_variant=1 (16-byte accesses, tail of 1-3 slots handled separately) and degree_sort (layout) are
-    experiments that stay off by default; whatever they do to speed, results must not move."""
-    for name in ("rgg_n16384_p1", "rgg_n65536_p1", "hand_loops_multi_p1", "hand_star41_p1", "hand_k66_p1", "hand_path16_p1"):
-        case = golden[name]
-        nv, parts, rowptr, edges = as_single(case)
-        for opts in ({"fold_variant": 1}, {"fold_variant": 1, "reorder": 1, "region_size": 64, "degree_sort": 1024}):
-            res = run_single(gpu, parts, rowptr, edges, nv, **opts)
-            assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, res["comm"])
