@@ -55,6 +55,18 @@ inline int mv_env_repeat() {
   return n < 1 ? 1 : n;
 }
 
+// MVGPU_SCAN_TIMES=1: print the duration of every scan launch of the last phase (ms) on stderr
+inline void mv_print_scan_times(mvgpu_ctx *ctx, int me) {
+  if (me != 0 || !std::getenv("MVGPU_SCAN_TIMES")) return;
+  int n = 0;
+  mvgpu_get_scan_times(ctx, 0, nullptr, &n);
+  std::vector<double> t(n);
+  if (n) mvgpu_get_scan_times(ctx, n, t.data(), &n);
+  std::fprintf(stderr, "SCAN_MS");
+  for (double x : t) std::fprintf(stderr, " %.3f", x * 1e3);
+  std::fprintf(stderr, "\n");
+}
+
 // The 6 scratch parameters (ssz ... rvdata) are caller-owned out-params that only the reference's
 // exchangeVertexReqs filled (dspl.hpp:1106-1272); the ghost lists now live in device memory, so they
 // are left empty.
@@ -77,6 +89,7 @@ inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph
   for (int rep = mv_env_repeat(); rep > 0; rep--)
     if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
   mvgpu_get_timings(ctx, &rc.timings);
+  mv_print_scan_times(ctx, me);
   if (rc.trace) {
     int n = 0;
     mvgpu_get_trace(ctx, 0, nullptr, &n);
@@ -113,6 +126,7 @@ inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, 
   for (int rep = mv_env_repeat(); rep > 0; rep--)
     if (mvgpu_louvain(ctx, lower, thresh, &iters, &mod)) mv_abort("mvgpu_louvain");
   mvgpu_get_timings(ctx, &rc.timings);
+  mv_print_scan_times(ctx, me);
   if (rc.trace) {
     int n = 0;
     mvgpu_get_trace(ctx, 0, nullptr, &n);

@@ -68,6 +68,7 @@ struct ScanParams {
   int lnv;
   int has_self;                    // any self loop in the shard (uniform branch)
   int heavy_deg;                   // degree > heavy_deg is left to the high-degree kernel (<= kECap)
+  int has_heavy;                   // the shard has such vertices at all (uniform fast path when it has none)
   int relabel;                     // vertices were renumbered for locality: ids are internal, tie-breaks use labels
   int cache_policy;                // bit2: L2 evict_first on the streamed arrays (tails, target writes); bits 0-1 unused
                                    // (evict_last hints on the gathered arrays were measured without effect and removed)
@@ -775,45 +776,24 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
 // i.e. updateRemoteCommunities), zero the update array for the next iteration (distCleanCWandCU)
 // and accumulate sum(degree^2) for the modularity (dspl.hpp:458-471, 978-1103, 473-486, 432).
 // ----------------------------------------------------------------------------------------------
-template <bool UNIT>
-__global__ void __launch_bounds__(256) k_fold(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, CommW *cinfo_w,
-                                              long long *usize, double *udeg, Acc *acc) {
-  unsigned long long a2u = 0;
+__global__ void __launch_bounds__(256) k_fold_w(int lnv, CommW *cinfo_w, long long *usize, double *udeg, Acc *acc) {
   double a2d = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < lnv; i += gridDim.x * blockDim.x) {
-    if (UNIT) {
-      uint32_t dg = cdeg[i];
-      const unsigned long long u = upd[i];
-      if (u) {                                   // u = dsize*2^32 + ddeg (exact two's-complement sum of the deltas)
-        const int ddeg = (int)(uint32_t)u;
-        const int dsize = (int)(((long long)u - (long long)ddeg) >> 32);
-        dg += (uint32_t)ddeg;
-        cdeg[i] = dg;
-        if (dsize) csize[i] += dsize;
-        upd[i] = 0;
-      }
-      a2u += (unsigned long long)dg * dg;
-    } else {
-      CommW c = cinfo_w[i];
-      const long long us = usize[i];
-      const double ud = udeg[i];
-      if (us != 0 || ud != 0.0) {
-        c.size += us; c.degree += ud;
-        cinfo_w[i] = c; usize[i] = 0; udeg[i] = 0.0;
-      }
-      a2d += c.degree * c.degree;
+    CommW c = cinfo_w[i];
+    const long long us = usize[i];
+    const double ud = udeg[i];
+    if (us != 0 || ud != 0.0) {
+      c.size += us; c.degree += ud;
+      cinfo_w[i] = c; usize[i] = 0; udeg[i] = 0.0;
     }
+    a2d += c.degree * c.degree;
   }
-  __shared__ unsigned long long su[8];
   __shared__ double sd[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (UNIT) { const unsigned long long s = warp_sum(a2u); if (lane == 0) su[wid] = s; }
-  else { const double s = warp_sum(a2d); if (lane == 0) sd[wid] = s; }
+  const double s = warp_sum(a2d);
+  if (lane == 0) sd[wid] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (UNIT) { unsigned long long s = 0; for (int w = 0; w < 8; w++) s += su[w]; atomicAdd(&acc->la2_u, s); }
-    else { double s = 0; for (int w = 0; w < 8; w++) s += sd[w]; atomicAdd(&acc->la2_d, s); }
-  }
+  if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; w++) t += sd[w]; atomicAdd(&acc->la2_d, t); }
 }
 
 // Modularity partials as doubles for the cross-rank all-reduce (MPI_Allreduce of 2 doubles, dspl.hpp:441).
@@ -893,6 +873,10 @@ __global__ void __launch_bounds__(256) k_extract_weights(const Edge16 *edges, lo
     weights[e] = __ldcs(&edges[e].weight);
 }
 
+__global__ void __launch_bounds__(256) k_fill_ones(double *w, long long n) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) w[e] = 1.0;
+}
+
 // same conversion for the compact upload format (int32 global tails, unit weights; see mvgpu_upload_shard)
 __global__ void __launch_bounds__(256) k_convert_tails32(const int32_t *gtails, long long lne, long long base, long long bound,
                                                          int32_t *tails, long long *remote_list, unsigned long long *remote_cursor) {
@@ -919,12 +903,13 @@ __global__ void __launch_bounds__(256) k_remap_ghost_tails(const Edge16 *edges, 
   }
 }
 
-__global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int lnv, uint32_t *rowptr, unsigned int *maxdeg,
-                                                  unsigned int *bad) {
+__global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int lnv, long long lne, uint32_t *rowptr,
+                                                  unsigned int *maxdeg, unsigned int *bad) {
   unsigned int md = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= lnv; i += gridDim.x * blockDim.x) {
     const long long r = rowptr64[i];
     rowptr[i] = (uint32_t)r;
+    if ((i == 0 && r != 0) || (i == lnv && r != lne)) *bad = 1;      // the scan kernels trust [rowptr[v], rowptr[v+1])
     if (i < lnv) {
       const long long d = rowptr64[i + 1] - r;
       if (d < 0) *bad = 1;
@@ -935,16 +920,25 @@ __global__ void __launch_bounds__(256) k_rowptr32(const long long *rowptr64, int
   if ((threadIdx.x & 31) == 0 && md) atomicMax(maxdeg, md);
 }
 
+// "Is this adjacency list strictly increasing by GLOBAL tail id?"  -- asked on slot ids: lower ranks' ghosts (slots
+// [lnv, lnv+nlow)) precede the rank's own vertices ([0, lnv)), which precede higher ranks' ghosts.  A shard whose
+// lists all pass has no parallel edges (duplicates would be adjacent), which the first-iteration kernel relies on.
+__device__ __forceinline__ bool tails_ascend(int a, int b, int lnv, int nlow) {
+  const int ka = a < lnv ? 1 : (a < lnv + nlow ? 0 : 2), kb = b < lnv ? 1 : (b < lnv + nlow ? 0 : 2);
+  return ka < kb || (ka == kb && a < b);
+}
+
 // distSumVertexDegree + distInitComm + self-loop weights (dspl.hpp:82-107, 132-149, 247-248/285)
-// Unit-weight fold, four community slots per thread and iteration (option fold_variant=1, experimental): same
-// arithmetic as k_fold<true>, 16-byte loads so that more bytes are in flight per thread.
+// Unit-weight fold (same job as k_fold_w on the packed integer arrays): four community slots per thread and
+// iteration with 16-byte accesses (measured against a one-slot-per-thread version: 1.80 -> 1.48 ms per phase at
+// config 2, profiles/README.md round 2).  u = dsize*2^32 + ddeg is the exact two's-complement sum of the deltas.
 __device__ __forceinline__ uint32_t fold_apply_unit(uint32_t dg, unsigned long long u, int32_t *csize_i) {
   const int ddeg = (int)(uint32_t)u;
   const int dsize = (int)(((long long)u - (long long)ddeg) >> 32);
   if (dsize) *csize_i += dsize;
   return dg + (uint32_t)ddeg;
 }
-__global__ void __launch_bounds__(256) k_fold_unit4(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, Acc *acc) {
+__global__ void __launch_bounds__(256) k_fold_unit(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, Acc *acc) {
   unsigned long long a2u = 0;
   const int n4 = lnv >> 2;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
@@ -985,14 +979,24 @@ __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, co
                                                      const double *weights, int32_t *cur, uint32_t *cdeg, int32_t *csize,
                                                      unsigned long long *upd, CommW *cinfo_w, long long *usize, double *udeg,
                                                      double *vdeg, int32_t *self_i, double *self_d, double *total_weight,
-                                                     unsigned int *has_self) {
+                                                     unsigned int *has_self, int nlow, unsigned int *unordered) {
   double tw_sum = 0.0;
   unsigned int any_self = 0;
+  bool bad = false;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
     const uint32_t e0 = rowptr[v], e1 = rowptr[v + 1];
     cur[v] = (int32_t)(base + v);
     if (UNIT) {
       int sl = 0;
+      if (unordered) {                       // original numbering: the lists can still be checked for order (see tails_ascend)
+        int prev = 0;
+        for (uint32_t e = e0; e < e1; e++) {
+          const int t = tails[e];
+          sl += (t == v);
+          if (e > e0 && !tails_ascend(prev, t, lnv, nlow)) bad = true;
+          prev = t;
+        }
+      } else
       for (uint32_t e = e0; e < e1; e++) sl += (tails[e] == v);
       self_i[v] = sl;
       any_self |= (sl != 0);
@@ -1018,6 +1022,7 @@ __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, co
   }
   tw_sum = warp_sum(tw_sum);
   any_self = __any_sync(0xffffffffu, any_self);
+  if (bad) *unordered = 1;
   if ((threadIdx.x & 31) == 0) {
     if (tw_sum != 0.0) atomicAdd(total_weight, tw_sum);
     if (any_self) atomicOr(has_self, 1u);
@@ -1040,42 +1045,63 @@ __global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *
 // kernels compare the original ids kept as labels.
 // key = level << 22 | region  (atomicMin: lowest level wins, then lowest region -> deterministic)
 // ----------------------------------------------------------------------------------------------
+#ifndef MV_BFS_SUB
+#define MV_BFS_SUB 4
+#endif
+#ifndef MV_BFS_DONE
+#define MV_BFS_DONE 0      // 0: keys only; 1: `done` bitmap lets the level sweep skip settled vertices; 2: it also filters the edge probes
+#endif
 constexpr unsigned int kBfsRegionBits = 22;
 constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
-                                               int region_stride, int max_levels, unsigned int *level_flags) {
+                                               int region_stride, int max_levels, unsigned int *level_flags, uint32_t *done) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   for (int v = gtid; v < lnv; v += gsz)
     key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
+  for (int w = gtid; w < (lnv + 31) / 32; w += gsz) done[w] = 0;
   grid.sync();
   const int lane = threadIdx.x & 31;
+  // `done` (compile-time option MV_BFS_DONE, off: measured slower at config 2, profiles/README.md round 2): one bit per
+  // vertex, set when the vertex has been expanded.  1: a warp skips the key load of 32 settled vertices in the level
+  // sweep; 2: an edge probe whose target is settled also skips the random key[] sector.  Keys still decide.
+  // Frontier vertices found by a warp are parked in shared memory and expanded MV_BFS_SUB at a time, 32 / MV_BFS_SUB lanes each,
+  // so that several adjacency reads and their dependent probes are in flight per warp.
+  constexpr int kBfsSub = MV_BFS_SUB, kBfsLanes = 32 / kBfsSub;
+  __shared__ uint32_t s_front[256 / 32][32][3];
+  uint32_t(*front)[3] = s_front[threadIdx.x >> 5];
   for (int level = 0; level < max_levels; level++) {
     bool any = false;
-    // every warp inspects 32 consecutive keys; the (few) frontier vertices among them are expanded by the
-    // whole warp, lanes over edges, so the random key[] probes of one vertex are in flight together
-    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
+    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {          // vb is a multiple of 32: one `done` word per warp step
+      const uint32_t dw = MV_BFS_DONE ? __ldcg(done + (vb >> 5)) : 0u;
+      if (dw == 0xffffffffu) continue;
       const int v = vb + lane;
       unsigned int k = kBfsUnreached;
-      if (v < lnv) k = __ldcg(key + v);
+      if (v < lnv && !((dw >> lane) & 1u)) k = __ldcg(key + v);
       const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
-      unsigned int m = __ballot_sync(0xffffffffu, active);
-      any |= (m != 0);
-      uint32_t r0 = 0, r1 = 0;
-      if (active) { r0 = rowptr[v]; r1 = rowptr[v + 1]; }
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const unsigned int kb = __shfl_sync(0xffffffffu, k, b);
-        const uint32_t e0 = __shfl_sync(0xffffffffu, r0, b), e1 = __shfl_sync(0xffffffffu, r1, b);
-        const unsigned int nk = ((unsigned int)(level + 1) << kBfsRegionBits) | (kb & ((1u << kBfsRegionBits) - 1));
-        for (uint32_t e = e0 + lane; e < e1; e += 32) {
+      const unsigned int m = __ballot_sync(0xffffffffu, active);
+      if (m == 0) continue;
+      any = true;
+      if (MV_BFS_DONE && lane == 0) __stcg(done + (vb >> 5), dw | m);
+      if (active) {
+        const int slot = __popc(m & ((1u << lane) - 1u));
+        front[slot][0] = ((unsigned int)(level + 1) << kBfsRegionBits) | (k & ((1u << kBfsRegionBits) - 1));
+        front[slot][1] = rowptr[v];
+        front[slot][2] = rowptr[v + 1];
+      }
+      __syncwarp();
+      const int cnt = __popc(m);
+      for (int i = lane / kBfsLanes; i < cnt; i += kBfsSub) {
+        const unsigned int nk = front[i][0];
+        const uint32_t e1 = front[i][2];
+        for (uint32_t e = front[i][1] + (lane % kBfsLanes); e < e1; e += kBfsLanes) {
           const int w = tails[e];
-          if (w < lnv && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
+          if (w < lnv && (MV_BFS_DONE < 2 || !((__ldcg(done + (w >> 5)) >> (w & 31)) & 1u)) && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
         }
       }
+      __syncwarp();
     }
     if (__syncthreads_or(any) && threadIdx.x == 0) level_flags[level] = 1;
     grid.sync();
@@ -1083,15 +1109,18 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
   }
 }
 
-// sort key: region major, level minor; unreached vertices (other components) last, in id order
-__global__ void __launch_bounds__(256) k_bfs_sortkeys(int lnv, const uint32_t *key, uint32_t *sortkey, int32_t *ids) {
+// sort key: region major, level minor (8 bits, deeper levels clamp: layout quality only); unreached vertices (other
+// components) carry `unreached_key` = all ones inside the sorted bit range and come last, in id order
+constexpr unsigned int kBfsLevelBits = 8;
+__global__ void __launch_bounds__(256) k_bfs_sortkeys(int lnv, const uint32_t *key, uint32_t *sortkey, int32_t *ids,
+                                                      unsigned int unreached_key) {
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
     const unsigned int k = key[v];
     unsigned int sk;
-    if (k == kBfsUnreached) sk = 0xFFFFFFFFu;
+    if (k == kBfsUnreached) sk = unreached_key;
     else {
-      const unsigned int region = k & ((1u << kBfsRegionBits) - 1), level = min(k >> kBfsRegionBits, 1023u);
-      sk = (region << 10) | level;
+      const unsigned int region = k & ((1u << kBfsRegionBits) - 1), level = min(k >> kBfsRegionBits, (1u << kBfsLevelBits) - 1u);
+      sk = (region << kBfsLevelBits) | level;
     }
     sortkey[v] = sk;
     ids[v] = v;
@@ -1114,18 +1143,21 @@ __global__ void __launch_bounds__(256) k_perm_inverse(int lnv, const int32_t *pe
 // edge order preserved (weighted sums keep the reference's summation order)
 __global__ void __launch_bounds__(256) k_permute_adj(int lnv, const int32_t *perm, const int32_t *inv, const uint32_t *rowptr_old,
                                                      const int32_t *tails_old, const double *w_old, const uint32_t *rowptr_new,
-                                                     int32_t *tails_new, double *w_new) {
+                                                     int32_t *tails_new, double *w_new, int nlow, unsigned int *unordered) {
   const int lane = threadIdx.x & 7;
   const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, ntiles = (gridDim.x * blockDim.x) >> 3;
+  bool bad = false;
   for (int i = tile; i < lnv; i += ntiles) {
     const int o = perm[i];
     const uint32_t s0 = rowptr_old[o], s1 = rowptr_old[o + 1], d0 = rowptr_new[i];
     for (uint32_t k = lane; k < s1 - s0; k += 8) {
       const int t = tails_old[s0 + k];
+      if (k && !tails_ascend(tails_old[s0 + k - 1], t, lnv, nlow)) bad = true;   // neighbour lane's element: an L1 hit
       tails_new[d0 + k] = (t < lnv) ? inv[t] : t;
       if (w_old) w_new[d0 + k] = w_old[s0 + k];
     }
   }
+  if (bad) *unordered = 1;
 }
 
 // average |tail - v| over a sample of edges: decides whether the given numbering already has locality

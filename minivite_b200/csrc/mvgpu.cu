@@ -26,7 +26,9 @@
 #include <vector>
 
 #include "../../include/mvgpu.h"
+#include "host_comm.hpp"
 #include "kernels.cuh"
+#include "scan_pipe.cuh"
 #include "nccl_dyn.h"
 #include "rgg_gpu.cuh"
 
@@ -63,6 +65,7 @@ template <typename T>
 struct DevBuf {              // grow-only device buffer (allocations are cached across runs); frees itself
   T *p = nullptr;
   size_t cap = 0;
+  unsigned gen = 0;          // bumped by every (re)allocation: cudaMalloc may hand the old address back for a new block
   DevBuf() = default;
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
@@ -74,6 +77,7 @@ struct DevBuf {              // grow-only device buffer (allocations are cached 
     if (n == 0) n = 1;
     CK(cudaMalloc(&p, n * sizeof(T)));
     cap = n;
+    gen++;
     return 0;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -93,8 +97,9 @@ struct mvgpu_ctx {
   int device = 0, rank = 0, nranks = 1;
   cudaStream_t stream = nullptr;
   int num_sms = 148;
-  // communicator
+  // communicator: NCCL, or the host transport (option host_transport=1) for the setup-time exchanges
   ncclComm_t comm = nullptr;
+  mvhost::HostComm hc;
   // input (reference format, device)
   long long nv_global = 0, lnv = 0, lne = 0, base = 0, bound = 0;
   std::vector<long long> parts;
@@ -141,7 +146,8 @@ struct mvgpu_ctx {
   DevBuf<double> udeg;
   DevBuf<Acc> acc;
   DevBuf<unsigned char> scratch;       // small device scalars
-  DevBuf<unsigned char> cub_tmp;
+  DevBuf<unsigned char> cub_tmp, coll_tmp;
+  DevBuf<long long> sorted_tmp;
   // ghosts
   DevBuf<long long> remote_list, ghost_gid, send_gid;
   DevBuf<int32_t> send_lid, send_buf;
@@ -153,6 +159,7 @@ struct mvgpu_ctx {
   DevBuf<unsigned long long> heavy_off;
   long long nheavy = 0, maxdeg = 0;
   int scan_has_self = 0, scan_heavy_deg = kECap;
+  bool simple_sorted = false;          // unit graph, adjacency lists strictly increasing (no parallel edges), no self loops
   // peers
   DevBuf<P2PState> p2p;
   P2PPeers pp;
@@ -165,13 +172,15 @@ struct mvgpu_ctx {
   bool peers_ready = false, ipc_valid = false;
   int peers_unit = -1;
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  unsigned last_gens[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_degree_sort = 0, opt_fold_variant = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
   double constant = 0.0;
   int32_t *d_final = nullptr;          // currComm at exit (points into comm_a/comm_b)
+  bool final_ready = false;            // final_orig holds the assignment of the last run in the caller's numbering
   std::vector<mvgpu_iter_trace> trace;
   std::vector<double> scan_times;
   mvgpu_timings tm;
@@ -185,34 +194,6 @@ struct mvgpu_ctx {
 };
 
 namespace {
-
-// Layout refinement on top of the BFS order (option "degree_sort" = window size, experimental, off by default):
-// inside every window of W consecutive positions the vertices are put in ascending degree order (stable), so the 32
-// lanes of a scan warp -- which walk their neighbour lists in lock step, trip count = longest list -- get lists of
-// similar length.  The window stays inside a few BFS regions, so gather locality is kept.  Layout only.
-template <int ITEMS>
-__global__ void __launch_bounds__(256) k_window_degree_sort(int lnv, const uint32_t *rowptr, int32_t *perm) {
-  using Sort = cub::BlockRadixSort<unsigned int, 256, ITEMS, int>;
-  __shared__ typename Sort::TempStorage tmp;
-  const int w0 = blockIdx.x * 256 * ITEMS;
-  unsigned int key[ITEMS];
-  int val[ITEMS];
-#pragma unroll
-  for (int k = 0; k < ITEMS; k++) {
-    const int pos = w0 + threadIdx.x * ITEMS + k;
-    if (pos < lnv) {
-      const int v = perm[pos];
-      val[k] = v;
-      key[k] = min(rowptr[v + 1] - rowptr[v], 126u);
-    } else { val[k] = -1; key[k] = 127u; }          // padding sorts behind every real vertex
-  }
-  Sort(tmp).Sort(key, val, 0, 7);
-#pragma unroll
-  for (int k = 0; k < ITEMS; k++) {
-    const int pos = w0 + threadIdx.x * ITEMS + k;
-    if (pos < lnv) perm[pos] = val[k];
-  }
-}
 
 int grid_for(long long n, int threads, int num_sms, int per_sm = 8) {
   long long b = (n + threads - 1) / threads;
@@ -237,13 +218,77 @@ struct Scalars {
   unsigned long long remote_cursor;
   unsigned int maxdeg, bad_rowptr, has_self, heavy_count;
   int nunique;
-  int pad;
+  unsigned int unordered;              // some adjacency list is not strictly increasing by global tail id
   double total_weight;
   double red2[2];
   unsigned long long tr2[2];
   long long counts[2 * kMaxRanks];
   unsigned long long span_sum, span_cnt;
 };
+
+// ---- setup-time collectives (a handful per run): NCCL on the library's stream, or the host transport ----------------
+int coll_sync(mvgpu_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return 0; }
+
+// element-wise sum / max of n <= 2*kMaxRanks int64 values held on the host, result on every rank
+int coll_allreduce_i64(mvgpu_ctx *c, long long *v, int n, bool is_max) {
+  if (c->nranks == 1) return 0;
+  if (c->hc.is_open()) {
+    if (is_max) c->hc.allreduce(v, n, [](long long a, long long b) { return a > b ? a : b; });
+    else c->hc.allreduce(v, n, [](long long a, long long b) { return a + b; });
+    return 0;
+  }
+  long long *d = reinterpret_cast<Scalars *>(c->scratch.p)->counts;
+  CK(cudaMemcpyAsync(d, v, sizeof(long long) * n, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllReduce(d, d, n, ncclInt64, is_max ? ncclMax : ncclSum, c->comm, c->stream));
+  CK(cudaMemcpyAsync(v, d, sizeof(long long) * n, cudaMemcpyDeviceToHost, c->stream));
+  return coll_sync(c);
+}
+// every rank contributes `bytes` from host memory; all[r * bytes ..] = rank r's contribution
+int coll_allgather(mvgpu_ctx *c, const void *mine, void *all, size_t bytes) {
+  if (c->hc.is_open()) { c->hc.allgather(mine, all, bytes); return 0; }
+  DevBuf<unsigned char> &d = c->coll_tmp;        // grow-only staging buffer: no allocation inside the timed setup after the first run
+  TRY(d.ensure(bytes * (c->nranks + 1)));
+  unsigned char *dm = d.p + bytes * c->nranks;
+  CK(cudaMemcpyAsync(dm, mine, bytes, cudaMemcpyHostToDevice, c->stream));
+  NK(g_nccl.AllGather(dm, d.p, bytes, ncclChar, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all, d.p, bytes * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  return coll_sync(c);
+}
+// all-to-all-v between device buffers with counts known on both sides (elements of `elem` bytes, 4 or 8).  NCCL: one
+// grouped send/recv round, left on the stream.  Host transport: staged through the shared segment (synchronous).
+int coll_alltoallv_dev(mvgpu_ctx *c, const void *d_send, const std::vector<long long> &scount, const std::vector<long long> &soff,
+                       void *d_recv, const std::vector<long long> &rcount, const std::vector<long long> &roff, size_t elem) {
+  const int n = c->nranks;
+  if (c->hc.is_open()) {
+    std::vector<size_t> sc(n), so(n), rc(n), ro(n);
+    for (int r = 0; r < n; r++) { sc[r] = (r == c->rank ? 0 : scount[r]) * elem; so[r] = soff[r] * elem; rc[r] = (r == c->rank ? 0 : rcount[r]) * elem; ro[r] = roff[r] * elem; }
+    const size_t sbytes = (size_t)soff[n] * elem, rbytes = (size_t)roff[n] * elem;
+    std::vector<unsigned char> hs(sbytes + 1), hr(rbytes + 1);
+    if (sbytes) CK(cudaMemcpyAsync(hs.data(), d_send, sbytes, cudaMemcpyDeviceToHost, c->stream));
+    TRY(coll_sync(c));
+    c->hc.alltoallv(hs.data(), sc.data(), so.data(), hr.data(), rc.data(), ro.data());
+    for (int r = 0; r < n; r++)
+      if (rc[r]) CK(cudaMemcpyAsync((unsigned char *)d_recv + ro[r], hr.data() + ro[r], rc[r], cudaMemcpyHostToDevice, c->stream));
+    return coll_sync(c);
+  }
+  const ncclDataType_t ty = elem == 8 ? ncclInt64 : ncclInt32;
+  NK(g_nccl.GroupStart());
+  for (int r = 0; r < n; r++) {
+    if (r == c->rank) continue;
+    if (scount[r]) NK(g_nccl.Send((const unsigned char *)d_send + soff[r] * elem, scount[r], ty, r, c->comm, c->stream));
+    if (rcount[r]) NK(g_nccl.Recv((unsigned char *)d_recv + roff[r] * elem, rcount[r], ty, r, c->comm, c->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+// everything enqueued on every rank's stream so far has completed when this returns
+int coll_barrier(mvgpu_ctx *c) {
+  if (c->nranks == 1) return coll_sync(c);
+  if (c->hc.is_open()) { TRY(coll_sync(c)); c->hc.barrier(); return 0; }
+  long long *d = reinterpret_cast<Scalars *>(c->scratch.p)->counts;
+  NK(g_nccl.AllReduce(d, d, 1, ncclInt64, ncclSum, c->comm, c->stream));
+  return coll_sync(c);
+}
 
 int set_graph(mvgpu_ctx *c, long long nv_global, const int64_t *parts, long long lnv, long long lne) {
   if (c->nranks > kMaxRanks) return fail("too many ranks");
@@ -278,15 +323,11 @@ int setup_peers(mvgpu_ctx *c, int unit) {
                     (void *)c->comm_a.p, (void *)c->comm_b.p, (void *)c->p2p.p};
   if (c->peers_ready) return 0;            // same graph, same buffers: tables are still valid
   // IPC handles are expensive to (re)open: skip the exchange when no rank's buffers moved since the last one
+  const unsigned gens[10] = {c->cdeg.gen, c->csize.gen, c->upd.gen, c->cinfo_w.gen, c->usize.gen, c->udeg.gen, c->lab.gen,
+                             c->comm_a.gen, c->comm_b.gen, c->p2p.gen};
   long long changed = c->ipc_valid ? 0 : 1;
-  for (int k = 0; k < 10; k++) if (ptrs[k] != c->last_ptrs[k]) changed = 1;
-  {
-    Scalars *d_sc = reinterpret_cast<Scalars *>(c->scratch.p);
-    CK(cudaMemcpyAsync(d_sc->counts, &changed, sizeof changed, cudaMemcpyHostToDevice, c->stream));
-    NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclMax, c->comm, c->stream));
-    CK(cudaMemcpyAsync(&changed, d_sc->counts, sizeof changed, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  for (int k = 0; k < 10; k++) if (ptrs[k] != c->last_ptrs[k] || (ptrs[k] && gens[k] != c->last_gens[k])) changed = 1;
+  TRY(coll_allreduce_i64(c, &changed, 1, true));
   if (changed) {
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   c->ipc_opened.clear();
@@ -298,25 +339,21 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     if (ptrs[k]) CK(cudaIpcGetMemHandle(&mine.h[k], ptrs[k]));
   }
   mine.pid = (int)getpid(); mine.device = c->device; mine.unit = unit;
-  DevBuf<PeerBlob> d_all;
-  TRY(d_all.ensure(c->nranks + 1));
-  CK(cudaMemcpyAsync(d_all.p + c->nranks, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
-  NK(g_nccl.AllGather(d_all.p + c->nranks, d_all.p, sizeof(PeerBlob), ncclChar, c->comm, c->stream));
   std::vector<PeerBlob> all(c->nranks);
-  CK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(PeerBlob) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  d_all.release();
+  TRY(coll_allgather(c, &mine, all.data(), sizeof(PeerBlob)));
   for (int r = 0; r < c->nranks; r++) {
     void *q[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (all[r].unit != unit) return fail("ranks disagree on the unit-weight path");
     if (r == c->rank) { for (int k = 0; k < 10; k++) q[k] = ptrs[k]; }
     else if (all[r].pid == mine.pid) {           // same process (threads): plain UVA pointers + peer access
-      int can = 0;
-      CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
-      if (!can) return fail("GPU " + std::to_string(c->device) + " cannot access peer GPU " + std::to_string(all[r].device));
-      cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
-      cudaGetLastError();
+      if (all[r].device != c->device) {          // ranks sharing one device need no peer mapping at all
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, c->device, all[r].device));
+        if (!can) return fail("GPU " + std::to_string(c->device) + " cannot access peer GPU " + std::to_string(all[r].device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+        cudaGetLastError();
+      }
       for (int k = 0; k < 10; k++) q[k] = (void *)all[r].raw[k];
     } else {
       for (int k = 0; k < 10; k++)
@@ -331,21 +368,14 @@ int setup_peers(mvgpu_ctx *c, int unit) {
     c->peer_comm[0][r] = (int32_t *)q[7]; c->peer_comm[1][r] = (int32_t *)q[8];
     c->pp.st[r] = (P2PState *)q[9];
   }
-  for (int k = 0; k < 10; k++) c->last_ptrs[k] = ptrs[k];
+  for (int k = 0; k < 10; k++) { c->last_ptrs[k] = ptrs[k]; c->last_gens[k] = gens[k]; }
   c->ipc_valid = true;
   }
   // where my send segments land in each peer's community array: its lnv + its receive offset for me
   {
-    DevBuf<long long> d_gb;
-    TRY(d_gb.ensure((size_t)c->nranks * (c->nranks + 1)));
     std::vector<long long> gb(c->nranks), allgb((size_t)c->nranks * c->nranks);
     for (int r = 0; r < c->nranks; r++) gb[r] = c->lnv + c->roff[r];
-    long long *mine_d = d_gb.p + (size_t)c->nranks * c->nranks;
-    CK(cudaMemcpyAsync(mine_d, gb.data(), sizeof(long long) * c->nranks, cudaMemcpyHostToDevice, c->stream));
-    NK(g_nccl.AllGather(mine_d, d_gb.p, c->nranks, ncclInt64, c->comm, c->stream));
-    CK(cudaMemcpyAsync(allgb.data(), d_gb.p, sizeof(long long) * allgb.size(), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    d_gb.release();
+    TRY(coll_allgather(c, gb.data(), allgb.data(), sizeof(long long) * c->nranks));
     for (int b = 0; b < 2; b++) {
       PushTable &t = c->push[b];
       t.nranks = c->nranks;
@@ -360,7 +390,7 @@ int setup_peers(mvgpu_ctx *c, int unit) {
 }
 
 template <bool UNIT, bool MULTI, bool TRACE>
-int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
+int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp, bool first) {
   const size_t smem = UNIT ? sizeof(int32_t) * 2 * kECap : sizeof(int32_t) * kECap + sizeof(double) * kECap;
   static bool attr_done = false;
   if (!attr_done) {
@@ -369,7 +399,21 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
-  if (tiles > 0) {
+  if (tiles > 0 && c->opt_scan_variant == 4) {
+    // persistent warps, TMA-fed double buffer (scan_pipe.cuh): one CTA slot per resident block, warps stride over groups
+    static int pw_ctas_per_sm = 0;
+    if (!pw_ctas_per_sm) {
+      CK(cudaFuncSetAttribute(k_scan_pw<UNIT, MULTI, TRACE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<UNIT>()));
+      CK(cudaFuncSetAttribute(k_scan_pw<UNIT, MULTI, TRACE, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<UNIT>()));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pw_ctas_per_sm, k_scan_pw<UNIT, MULTI, TRACE, false>, kPwWarps * 32, pw_smem_bytes<UNIT>()));
+      if (pw_ctas_per_sm < 1) return fail("k_scan_pw cannot be made resident");
+    }
+    const int ngroups = (int)((c->lnv + 31) / 32);
+    const int grid = std::min((ngroups + kPwWarps - 1) / kPwWarps, pw_ctas_per_sm * c->num_sms);
+    if (UNIT && first) k_scan_pw<UNIT, MULTI, TRACE, UNIT><<<grid, kPwWarps * 32, pw_smem_bytes<UNIT>(), c->stream>>>(sp, ngroups);
+    else k_scan_pw<UNIT, MULTI, TRACE, false><<<grid, kPwWarps * 32, pw_smem_bytes<UNIT>(), c->stream>>>(sp, ngroups);
+    c->tm.kernel_launches++; c->tm.scan_launches++;
+  } else if (tiles > 0) {
     if (c->opt_scan_variant == 0) k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
     else k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
@@ -382,9 +426,9 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp) {
   return 0;
 }
 
-int launch_scan(mvgpu_ctx *c, const ScanParams &sp) {
+int launch_scan(mvgpu_ctx *c, const ScanParams &sp, bool first) {
   const bool multi = c->nranks > 1, tr = c->opt_trace != 0;
-#define MV_CASE(U, M, T) if (c->unit == U && multi == M && tr == T) return launch_scan_t<U, M, T>(c, sp);
+#define MV_CASE(U, M, T) if (c->unit == U && multi == M && tr == T) return launch_scan_t<U, M, T>(c, sp, first);
   MV_CASE(true, false, false) MV_CASE(true, false, true) MV_CASE(true, true, false) MV_CASE(true, true, true)
   MV_CASE(false, false, false) MV_CASE(false, false, true) MV_CASE(false, true, false) MV_CASE(false, true, true)
 #undef MV_CASE
@@ -392,6 +436,7 @@ int launch_scan(mvgpu_ctx *c, const ScanParams &sp) {
 }
 
 int exchange_ghosts(mvgpu_ctx *c, int32_t *comm);
+int final_in_caller_order(mvgpu_ctx *c);
 
 // ---- setup: reference-format arrays -> compact graph, ghosts, init ------------------------------
 int setup_run(mvgpu_ctx *c) {
@@ -408,7 +453,7 @@ int setup_run(mvgpu_ctx *c) {
   const bool compact_in = c->d_tails32 != nullptr;
   const bool fused_stats = !compact_in && c->nranks == 1;      // single rank: statistics ride on the conversion pass
   if (fused_stats) {
-    TRY(c->tails.ensure(lne));
+    TRY(c->tails.ensure(lne + 4));
     k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, c->tails.p,
                                                               nullptr, nullptr, nullptr, &d_sc->st);
     c->tm.kernel_launches++;
@@ -416,31 +461,45 @@ int setup_run(mvgpu_ctx *c) {
     k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
     c->tm.kernel_launches++;
   }
-  TRY(c->rowptr.ensure(lnv + 1));
-  k_rowptr32<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>(c->d_rowptr64, (int)lnv, c->rowptr.p, &d_sc->maxdeg, &d_sc->bad_rowptr);
+  TRY(c->rowptr.ensure(lnv + 1 + 40));        // + slack: the scan's row-offset bulk copies read 36 entries per group
+  k_rowptr32<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>(c->d_rowptr64, (int)lnv, lne, c->rowptr.p, &d_sc->maxdeg, &d_sc->bad_rowptr);
   c->tm.kernel_launches++;
   CK(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (compact_in) { h.st.nremote = (unsigned long long)c->in_nremote; h.st.nonunit = 0; h.st.bad_tail = 0; }
-  if (h.st.bad_tail) return fail("edge tail outside [0, nv)");
-  if (h.bad_rowptr) return fail("edge_indices not monotone");
-  if (c->nranks == 1 && h.st.nremote) return fail("non-local tail in a single-rank graph");
+  // input errors are agreed on across ranks before anybody returns: a rank that left alone would leave its peers
+  // blocked in the next collective
+  std::string input_err;
+  if (h.st.bad_tail) input_err = "edge tail outside [0, nv)";
+  else if (h.bad_rowptr) input_err = "edge_indices malformed (must start at 0, end at lne and never decrease)";
+  else if (c->nranks == 1 && h.st.nremote) input_err = "non-local tail in a single-rank graph";
   c->maxdeg = h.maxdeg;
   int unit = (!h.st.nonunit && !c->opt_force_weighted) ? 1 : 0;
-  if (compact_in && !unit) return fail("force_weighted needs the full edge records: set compact_upload=0");
+  if (input_err.empty() && compact_in && !unit) input_err = "force_weighted needs the full edge records: set compact_upload=0";
 
   // global agreement on the path + on 2m < 2^31 needs the total weight; the weight total itself comes
   // from the vertex-init kernel below, so first settle `unit` from the flags (ne bound checked after).
   long long ne_global = lne;
   if (c->nranks > 1) {
-    long long hv[2] = {unit ? 0 : 1, lne};
-    CK(cudaMemcpyAsync(d_sc->counts, hv, sizeof hv, cudaMemcpyHostToDevice, s));
-    NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 2, ncclInt64, ncclSum, c->comm, s));
-    CK(cudaMemcpyAsync(hv, d_sc->counts, sizeof hv, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // exported (peer-mapped) arrays that this run may have to grow: CUDA IPC requires every peer to close its
+    // mapping before the owner frees the block, so that is agreed on here and done collectively
+    const size_t need_v = (size_t)lnv, need_s = (size_t)(lnv + (long long)h.st.nremote);
+    const bool grow = c->ipc_valid && ((c->cdeg.p && c->cdeg.cap < need_v) || (c->cinfo_w.p && c->cinfo_w.cap < need_v) ||
+                                       (c->lab.p && c->lab.cap < need_v) || c->comm_a.cap < need_s || c->comm_b.cap < need_s);
+    long long hv[4] = {unit ? 0 : 1, lne, input_err.empty() ? 0 : 1, grow ? 1 : 0};
+    TRY(coll_allreduce_i64(c, hv, 4, false));
     unit = hv[0] == 0;
     ne_global = hv[1];
+    if (hv[2] && input_err.empty()) input_err = "another rank rejected its shard";
+    if (hv[3]) {
+      for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+      c->ipc_opened.clear();
+      c->ipc_valid = false;
+      c->peers_ready = false;
+      TRY(coll_barrier(c));                       // all mappings are closed before any owner reallocates
+    }
   }
+  if (!input_err.empty()) return fail(input_err);
   if (unit && ne_global >= (1LL << 31)) unit = 0;   // packed 32-bit degree deltas need 2m < 2^31
   c->unit = unit != 0;
 
@@ -452,17 +511,23 @@ int setup_run(mvgpu_ctx *c) {
   const double *src_weights = nullptr;
   if (compact_in && c->nranks == 1) {
     src_tails = c->d_tails32;                       // global id == local slot: the uploaded array is used as is (read-only)
+    if (!c->unit) {                                 // 2m >= 2^31: fp64 path on a shard that arrived without weights
+      TRY(c->weights.ensure(lne + 4));
+      k_fill_ones<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->weights.p, lne);
+      c->tm.kernel_launches++;
+      src_weights = c->weights.p;
+    }
   } else if (fused_stats) {
     src_tails = c->tails.p;                         // converted by the fused pass above
     if (!c->unit) {
-      TRY(c->weights.ensure(lne));
+      TRY(c->weights.ensure(lne + 4));
       k_extract_weights<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->weights.p);
       c->tm.kernel_launches++;
       src_weights = c->weights.p;
     }
   } else {
-    TRY(c->tails.ensure(lne));
-    if (!c->unit) TRY(c->weights.ensure(lne));
+    TRY(c->tails.ensure(lne + 4));
+    if (!c->unit) TRY(c->weights.ensure(lne + 4));
     if (compact_in)
       k_convert_tails32<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_tails32, lne, c->base, c->bound, c->tails.p,
                                                                   nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
@@ -471,6 +536,10 @@ int setup_run(mvgpu_ctx *c) {
                                                                 c->unit ? nullptr : c->weights.p,
                                                                 nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor, nullptr);
     c->tm.kernel_launches++;
+    if (compact_in && !c->unit) {                   // a peer's shard is weighted (or 2m >= 2^31): this one's weights are all 1.0
+      k_fill_ones<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->weights.p, lne);
+      c->tm.kernel_launches++;
+    }
     src_tails = c->tails.p;
     src_weights = c->unit ? nullptr : c->weights.p;
   }
@@ -481,7 +550,7 @@ int setup_run(mvgpu_ctx *c) {
   c->roff.assign(c->nranks + 1, 0); c->soff.assign(c->nranks + 1, 0);
   if (c->nranks > 1) {
     if (nremote) {
-      DevBuf<long long> sorted;
+      DevBuf<long long> &sorted = c->sorted_tmp;   // grow-only: no cudaMalloc/cudaFree inside the timed setup after the first run
       TRY(sorted.ensure(nremote));
       TRY(c->ghost_gid.ensure(nremote));
       size_t tb1 = 0, tb2 = 0;
@@ -498,7 +567,6 @@ int setup_run(mvgpu_ctx *c) {
       int nu = 0;
       CK(cudaMemcpyAsync(&nu, &d_sc->nunique, sizeof nu, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      sorted.release();
       c->nghost = nu;
       if (lnv + c->nghost >= (1LL << 31)) return fail("lnv + nghost >= 2^31");
       k_remap_ghost_tails<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(compact_in ? nullptr : c->d_edges, c->d_tails32, lne, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
@@ -515,29 +583,19 @@ int setup_run(mvgpu_ctx *c) {
     }
     for (int r = 0; r < c->nranks; r++) c->roff[r + 1] = c->roff[r] + c->rcount[r];
     // tell every owner how many of its vertices I ghost (MPI_Alltoall of sizes, dspl.hpp:1184)
-    long long *d_cnt = d_sc->counts;
-    CK(cudaMemcpyAsync(d_cnt, c->rcount.data(), sizeof(long long) * c->nranks, cudaMemcpyHostToDevice, s));
-    NK(g_nccl.GroupStart());
-    for (int r = 0; r < c->nranks; r++) {
-      NK(g_nccl.Send(d_cnt + r, 1, ncclInt64, r, c->comm, s));
-      NK(g_nccl.Recv(d_cnt + kMaxRanks + r, 1, ncclInt64, r, c->comm, s));
+    {
+      std::vector<long long> allc((size_t)c->nranks * c->nranks);
+      TRY(coll_allgather(c, c->rcount.data(), allc.data(), sizeof(long long) * c->nranks));
+      for (int r = 0; r < c->nranks; r++) c->scount[r] = allc[(size_t)r * c->nranks + c->rank];
     }
-    NK(g_nccl.GroupEnd());
-    CK(cudaMemcpyAsync(c->scount.data(), d_cnt + kMaxRanks, sizeof(long long) * c->nranks, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     for (int r = 0; r < c->nranks; r++) c->soff[r + 1] = c->soff[r] + c->scount[r];
     c->nsend = c->soff[c->nranks];
     // ship the ghost id lists to their owners (dspl.hpp:1228-1252); they become the owners' send lists
     TRY(c->send_gid.ensure(c->nsend));
     TRY(c->send_lid.ensure(c->nsend));
     TRY(c->send_buf.ensure(c->nsend));
-    NK(g_nccl.GroupStart());
-    for (int r = 0; r < c->nranks; r++) {
-      if (r == c->rank) continue;
-      if (c->rcount[r]) NK(g_nccl.Send(c->ghost_gid.p + c->roff[r], c->rcount[r], ncclInt64, r, c->comm, s));
-      if (c->scount[r]) NK(g_nccl.Recv(c->send_gid.p + c->soff[r], c->scount[r], ncclInt64, r, c->comm, s));
-    }
-    NK(g_nccl.GroupEnd());
+    TRY(c->ghost_gid.ensure(c->nghost));
+    TRY(coll_alltoallv_dev(c, c->ghost_gid.p, c->rcount, c->roff, c->send_gid.p, c->scount, c->soff, sizeof(long long)));
     if (c->nsend) {
       k_gid_to_lid<<<grid_for(c->nsend, 256, nsm), 256, 0, s>>>(c->send_gid.p, (int)c->nsend, c->base, c->send_lid.p);
       c->tm.kernel_launches++;
@@ -561,10 +619,7 @@ int setup_run(mvgpu_ctx *c) {
     int any = want;
     if (c->nranks > 1) {
       long long hv = want;
-      CK(cudaMemcpyAsync(d_sc->counts, &hv, sizeof hv, cudaMemcpyHostToDevice, s));
-      NK(g_nccl.AllReduce(d_sc->counts, d_sc->counts, 1, ncclInt64, ncclMax, c->comm, s));
-      CK(cudaMemcpyAsync(&hv, d_sc->counts, sizeof hv, cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
+      TRY(coll_allreduce_i64(c, &hv, 1, true));
       any = hv != 0;
     }
     c->relabel = any;                       // labels are needed everywhere as soon as one rank renumbers
@@ -573,8 +628,8 @@ int setup_run(mvgpu_ctx *c) {
       CK(cudaEventRecord(r0, s));
       TRY(c->perm.ensure(lnv)); TRY(c->inv.ensure(lnv)); TRY(c->lab.ensure(lnv)); TRY(c->ids.ensure(lnv));
       TRY(c->bfs_key.ensure(lnv)); TRY(c->sortkey.ensure(lnv)); TRY(c->sortkey2.ensure(lnv));
-      TRY(c->deg_new.ensure(lnv + 1)); TRY(c->rowptr2.ensure(lnv + 1)); TRY(c->tails2.ensure(lne));
-      if (!c->unit) TRY(c->weights2.ensure(lne));
+      TRY(c->deg_new.ensure(lnv + 1)); TRY(c->rowptr2.ensure(lnv + 1 + 40)); TRY(c->tails2.ensure(lne + 4));
+      if (!c->unit) TRY(c->weights2.ensure(lne + 4));
       const int max_levels = 1023;
       TRY(c->level_flags.ensure(max_levels + 1));
       CK(cudaMemsetAsync(c->level_flags.p, 0, sizeof(unsigned int) * (max_levels + 1), s));
@@ -583,28 +638,26 @@ int setup_run(mvgpu_ctx *c) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msbfs, 256, 0));
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
+        TRY(c->bfs_visited.ensure((size_t)(lnv + 31) / 32 + 1));
         const uint32_t *rp = src_rowptr; const int32_t *tl = src_tails; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
+        uint32_t *done = c->bfs_visited.p;
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf, &done};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
-        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p);
+        // sort by (region, level): only the bits that can be set take part (one radix pass less than a 32-bit sort)
+        const long long nregions = (lnv + stride - 1) / stride;
+        int sort_bits = (int)kBfsLevelBits;
+        while ((1LL << (sort_bits - (int)kBfsLevelBits)) <= nregions && sort_bits < 32) sort_bits++;
+        const unsigned int unreached_key = sort_bits >= 32 ? 0xFFFFFFFFu : ((1u << sort_bits) - 1u);
+        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->ids.p, unreached_key);
         size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s);
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, sort_bits, s);
         TRY(c->cub_tmp.ensure(tb));
         tb = c->cub_tmp.cap;
-        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, 32, s));
+        CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, c->sortkey.p, c->sortkey2.p, c->ids.p, c->perm.p, (int)lnv, 0, sort_bits, s));
         c->tm.kernel_launches += 3;
-        if (c->opt_degree_sort) {
-          const int items = c->opt_degree_sort / 256;
-          const int nb = (int)((lnv + c->opt_degree_sort - 1) / c->opt_degree_sort);
-          if (items == 1) k_window_degree_sort<1><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
-          else if (items == 2) k_window_degree_sort<2><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
-          else if (items == 4) k_window_degree_sort<4><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
-          else k_window_degree_sort<8><<<nb, 256, 0, s>>>((int)lnv, src_rowptr, c->perm.p);
-          c->tm.kernel_launches++;
-        }
       } else {
         // another rank renumbers, this one keeps its order: identity permutation, labels still required
-        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->perm.p);
+        k_bfs_sortkeys<<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->bfs_key.p, c->sortkey.p, c->perm.p, 0xFFFFFFFFu);
         c->tm.kernel_launches++;
       }
       k_perm_inverse<<<grid_for(lnv + 1, 256, nsm), 256, 0, s>>>((int)lnv, c->perm.p, c->base, c->inv.p, c->lab.p, src_rowptr, c->deg_new.p);
@@ -616,7 +669,8 @@ int setup_run(mvgpu_ctx *c) {
         tb = c->cub_tmp.cap;
         CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, c->deg_new.p, c->rowptr2.p, (int)lnv + 1, s));
         k_permute_adj<<<grid_for(lnv * 8, 256, nsm, 16), 256, 0, s>>>((int)lnv, c->perm.p, c->inv.p, src_rowptr, src_tails, src_weights,
-                                                                    c->rowptr2.p, c->tails2.p, c->unit ? nullptr : c->weights2.p);
+                                                                    c->rowptr2.p, c->tails2.p, c->unit ? nullptr : c->weights2.p,
+                                                                    (int)c->roff[c->rank], &d_sc->unordered);
         c->tm.kernel_launches += 2;
         src_rowptr = c->rowptr2.p;
         src_tails = c->tails2.p;
@@ -646,18 +700,21 @@ int setup_run(mvgpu_ctx *c) {
   if (c->unit)
     k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, nullptr, c->comm_a.p,
                                                               c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
-                                                              c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self);
+                                                              c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self,
+                                                              (int)c->roff[c->rank], c->reordered ? nullptr : &d_sc->unordered);
   else
     k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, c->a_weights, c->comm_a.p,
                                                                nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
-                                                               nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self);
+                                                               nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self, 0, nullptr);
   c->tm.kernel_launches++;
   // ghosts start in their own (internal) singleton community, which only the owner knows after renumbering:
   // fetch it with the same all-to-all-v the iterations use
   if (c->nranks > 1) TRY(exchange_ghosts(c, c->comm_a.p));
 
   // high-degree vertices
-  const long long heavy_deg = (c->opt_force_heavy_deg > 0) ? std::min<long long>(c->opt_force_heavy_deg, kECap) : kECap;
+  // largest degree the tile kernels take: one staging buffer (minus the 16-byte alignment slack of the bulk copies)
+  const long long tile_cap = c->opt_scan_variant == 4 ? (c->unit ? PwCap<true>::value : PwCap<false>::value) - 4 : kECap;
+  const long long heavy_deg = (c->opt_force_heavy_deg > 0) ? std::min<long long>(c->opt_force_heavy_deg, tile_cap) : tile_cap;
   c->nheavy = 0;
   if (c->maxdeg > heavy_deg) {
     TRY(c->heavy_list.ensure(lnv));
@@ -666,11 +723,13 @@ int setup_run(mvgpu_ctx *c) {
   }
 
   // 1/(2m): MPI_Allreduce of the local degree sums (dspl.hpp:109-130)
-  if (c->nranks > 1) NK(g_nccl.AllReduce(&d_sc->total_weight, &d_sc->total_weight, 1, ncclDouble, ncclSum, c->comm, s));
+  if (c->nranks > 1 && !c->hc.is_open()) NK(g_nccl.AllReduce(&d_sc->total_weight, &d_sc->total_weight, 1, ncclDouble, ncclSum, c->comm, s));
   CK(cudaMemcpyAsync(&h, d_sc, sizeof h, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (c->nranks > 1 && c->hc.is_open()) c->hc.allreduce(&h.total_weight, 1, [](double a, double b) { return a + b; });
   c->constant = 1.0 / h.total_weight;
   const int has_self = h.has_self ? 1 : 0;
+  c->simple_sorted = c->unit && !h.unordered && !has_self;
   if (c->maxdeg > heavy_deg) {
     c->nheavy = h.heavy_count;
     std::vector<int32_t> hl(c->nheavy);
@@ -711,19 +770,14 @@ int exchange_ghosts(mvgpu_ctx *c, int32_t *comm) {
     k_pack_send<<<grid_for(c->nsend, 256, c->num_sms), 256, 0, s>>>(comm, c->send_lid.p, (int)c->nsend, c->send_buf.p);
     c->tm.kernel_launches++;
   }
-  NK(g_nccl.GroupStart());
-  for (int r = 0; r < c->nranks; r++) {
-    if (r == c->rank) continue;
-    if (c->scount[r]) NK(g_nccl.Send(c->send_buf.p + c->soff[r], c->scount[r], ncclInt32, r, c->comm, s));
-    if (c->rcount[r]) NK(g_nccl.Recv(comm + c->lnv + c->roff[r], c->rcount[r], ncclInt32, r, c->comm, s));
-  }
-  NK(g_nccl.GroupEnd());
-  return 0;
+  std::vector<long long> roff_slots(c->roff);
+  return coll_alltoallv_dev(c, c->send_buf.p, c->scount, c->soff, comm + c->lnv, c->rcount, roff_slots, sizeof(int32_t));
 }
 
 int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, double *mod_out) {
   if (!c->have_graph) return fail("no graph uploaded");
-  if (c->nranks > 1 && !c->comm) return fail("mvgpu_comm_init has not been called");
+  if (c->nranks > 1 && !c->comm && !c->hc.is_open()) return fail("mvgpu_comm_init has not been called");
+  if (c->nranks > 1 && !c->comm && c->opt_comm_mode != 1) return fail("comm_mode=0 (NCCL data plane) needs the NCCL communicator: host_transport=1 supports comm_mode=1 only");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   memset(&c->tm, 0, sizeof c->tm);
@@ -740,7 +794,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   int32_t *cur = c->comm_a.p, *tgt = c->comm_b.p;
   ScanParams sp;
   memset(&sp, 0, sizeof sp);
-  sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.base = c->base;
+  sp.lnv = (int)c->lnv; sp.has_self = c->scan_has_self; sp.heavy_deg = c->scan_heavy_deg; sp.has_heavy = c->nheavy > 0; sp.base = c->base;
   sp.cache_policy = c->opt_cache_policy;
   sp.relabel = c->relabel;
   sp.rowptr = c->a_rowptr; sp.tails = c->a_tails; sp.weights = c->unit ? nullptr : c->a_weights;
@@ -764,7 +818,8 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     sp.cur = cur; sp.tgt = tgt; sp.acc = acc;
     cudaEvent_t e0 = get_event(c, ev++), e1 = get_event(c, ev++), e2 = get_event(c, ev++), e3 = get_event(c, ev++);
     CK(cudaEventRecord(e0, s));
-    TRY(launch_scan(c, sp));
+    // iteration 1 of a simple graph: every community is a singleton (scan_pipe.cuh, FIRST)
+    TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant == 4));
     CK(cudaEventRecord(e1, s));
     const bool p2p = c->nranks > 1 && c->opt_comm_mode == 1;
     if (c->nranks > 1) {
@@ -783,10 +838,8 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       }
     }
     CK(cudaEventRecord(e2, s));
-    if (c->unit && c->opt_fold_variant == 1)
-      k_fold_unit4<<<grid_for((c->lnv >> 2) + 1, 256, c->num_sms, 8), 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, acc);
-    else if (c->unit) k_fold<true><<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, acc);
-    else k_fold<false><<<fold_grid, 256, 0, s>>>((int)c->lnv, nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
+    if (c->unit) k_fold_unit<<<grid_for((c->lnv >> 2) + 1, 256, c->num_sms, 8), 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, acc);
+    else k_fold_w<<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
     c->tm.kernel_launches++;
     CK(cudaEventRecord(e3, s));
     double e_xx, a2_x;
@@ -839,8 +892,19 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   }
   cudaEvent_t e_end = get_event(c, ev++);
   CK(cudaEventRecord(e_end, s));
-  CK(cudaEventSynchronize(e_end));
   c->d_final = cur;
+  c->final_ready = false;
+  if (c->nranks > 1) {
+    // the assignment in the caller's numbering needs the label arrays of the PEERS (a community may be owned by another
+    // rank): resolve it now, while every rank is still inside this call, and leave together -- afterwards a rank may
+    // free its arrays (mvgpu_destroy) without a peer still reading them.  Outside the timed region, like the
+    // reference's output code is outside its timer.
+    TRY(final_in_caller_order(c));
+    if (c->opt_comm_mode == 1) { k_p2p_barrier<<<1, 32, 0, s>>>(c->pp, ++c->p2p_epoch); c->tm.kernel_launches++; }
+    else TRY(coll_barrier(c));
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaEventSynchronize(e_end));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e_begin, e_end)); c->tm.total_s = ms * 1e-3;
   CK(cudaEventElapsedTime(&ms, e_begin, e_setup)); c->tm.setup_s = ms * 1e-3;
@@ -858,6 +922,20 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   c->tm.h2d_bytes = c->h2d_bytes;
   *iters_out = numIters;                                       // dspl.hpp:1430
   *mod_out = prevMod;                                          // dspl.hpp:1440
+  return 0;
+}
+
+// currComm in the caller's vertex numbering, as labels (original global ids)
+int final_in_caller_order(mvgpu_ctx *c) {
+  if (c->final_ready) return 0;
+  CK(cudaSetDevice(c->device));
+  TRY(c->final_orig.ensure(c->lnv));
+  c->final_ready = true;
+  if (c->lnv == 0) return 0;
+  const int32_t *perm = c->reordered ? c->perm.p : nullptr;
+  if (c->nranks > 1) k_final_labels<true><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
+  else k_final_labels<false><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -899,6 +977,24 @@ int mvgpu_create(mvgpu_ctx **out, int device, int rank, int nranks) {
   CK(cudaMallocHost(&c->h_pin, 4096));
   memset(&c->tm, 0, sizeof c->tm);
   memset(&c->pt, 0, sizeof c->pt);
+  // developer knob: MVGPU_OPTIONS="name=value,name=value" presets options for every context of the process
+  if (const char *e = getenv("MVGPU_OPTIONS")) {
+    std::string all(e);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string kv = all.substr(pos, end - pos);
+      pos = end + 1;
+      const size_t eq = kv.find('=');
+      if (kv.empty()) continue;
+      if (eq == std::string::npos || mvgpu_set_option(c, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1))) {
+        const std::string msg = "MVGPU_OPTIONS: bad entry '" + kv + "'" + (eq == std::string::npos ? "" : ": " + g_err);
+        mvgpu_destroy(c);
+        return fail(msg);
+      }
+    }
+  }
   *out = c;
   return 0;
 }
@@ -909,6 +1005,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
   if (c->comm) g_nccl.CommDestroy(c->comm);
+  c->hc.close_comm();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->in_tails32.release(); c->wide.release();
@@ -917,7 +1014,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
-  c->scratch.release(); c->cub_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
+  c->scratch.release(); c->cub_tmp.release(); c->coll_tmp.release(); c->sorted_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
   c->bfs_key.release(); c->bfs_visited.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
   c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
   c->weights2.release(); c->level_flags.release();
@@ -932,7 +1029,13 @@ int mvgpu_destroy(mvgpu_ctx *c) {
 
 int mvgpu_get_unique_id(void *id128) {
   static_assert(sizeof(ncclUniqueId) == MVGPU_UNIQUE_ID_BYTES, "ncclUniqueId size");
-  if (!mvnccl::load(g_nccl, g_err)) return 1;
+  if (!mvnccl::load(g_nccl, g_err)) {
+    // no NCCL in this process: a random id still names the host transport's rendezvous segment
+    FILE *f = fopen("/dev/urandom", "rb");
+    if (!f || fread(id128, 1, MVGPU_UNIQUE_ID_BYTES, f) != MVGPU_UNIQUE_ID_BYTES) { if (f) fclose(f); return 1; }
+    fclose(f);
+    return 0;
+  }
   ncclUniqueId id;
   NK(g_nccl.GetUniqueId(&id));
   memcpy(id128, &id, sizeof id);
@@ -942,6 +1045,11 @@ int mvgpu_get_unique_id(void *id128) {
 int mvgpu_comm_init(mvgpu_ctx *c, const void *id128) {
   if (!c) return fail("null ctx");
   if (c->nranks == 1) return 0;
+  if (c->opt_host_transport) {                    // setup exchanges through shared memory; ranks may share a device
+    std::string err;
+    if (c->hc.open(id128, c->rank, c->nranks, err)) return fail(err);
+    return 0;
+  }
   if (!mvnccl::load(g_nccl, g_err)) return 1;
   CK(cudaSetDevice(c->device));
   ncclUniqueId id;
@@ -967,7 +1075,7 @@ static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const vo
     if (cudaMallocHost(&c->h_stage, sizeof(int32_t) * (size_t)lne) != cudaSuccess) { cudaGetLastError(); return 1; }
     c->h_stage_cap = (size_t)lne;
   }
-  if (c->in_tails32.ensure(lne)) return -1;
+  if (c->in_tails32.ensure(lne + 4)) return -1;
   int32_t *stage = reinterpret_cast<int32_t *>(c->h_stage);
   const long long base = c->base, bound = c->bound;
   const int nthreads = (int)std::max<long long>(1, std::min<long long>(c->opt_host_threads > 0 ? c->opt_host_threads : 8, nchunks));
@@ -1156,18 +1264,6 @@ int mvgpu_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters, double 
   return run_louvain(c, lower, thresh, iters, modularity);
 }
 
-// currComm in the caller's vertex numbering, as labels (original global ids)
-static int final_in_caller_order(mvgpu_ctx *c) {
-  CK(cudaSetDevice(c->device));
-  TRY(c->final_orig.ensure(c->lnv));
-  if (c->lnv == 0) return 0;
-  const int32_t *perm = c->reordered ? c->perm.p : nullptr;
-  if (c->nranks > 1) k_final_labels<true><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
-  else k_final_labels<false><<<grid_for(c->lnv, 256, c->num_sms), 256, 0, c->stream>>>((int)c->lnv, c->d_final, perm, c->last_sp, c->final_orig.p);
-  CK(cudaGetLastError());
-  return 0;
-}
-
 int mvgpu_get_communities_device(mvgpu_ctx *c, const int32_t **d_out) {
   if (!c || !c->d_final) return fail("no result yet");
   TRY(final_in_caller_order(c));
@@ -1230,12 +1326,8 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;
   else if (n == "compact_upload") c->opt_compact_upload = (int)value;
   else if (n == "host_threads") c->opt_host_threads = (int)value;
-  else if (n == "fold_variant") c->opt_fold_variant = (int)value;
-  else if (n == "degree_sort") {
-    if (value != 0 && value != 256 && value != 512 && value != 1024 && value != 2048)
-      return fail("degree_sort must be 0, 256, 512, 1024 or 2048");
-    c->opt_degree_sort = (int)value;
-  }
+  else if (n == "first_iter") c->opt_first_iter = value != 0;
+  else if (n == "host_transport") { if (c->comm || c->hc.is_open()) return fail("host_transport must be set before mvgpu_comm_init"); c->opt_host_transport = value != 0; }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;

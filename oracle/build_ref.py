@@ -20,7 +20,12 @@ Hooks (all on stderr / side files, all off unless the env var is set):
   always              rank 0 prints ``RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d``
                       to stderr next to the reference's own report block (main.cpp:178)
 
-Usage: python oracle/build_ref.py [--ref /root/reference] [--force]
+``--gpu`` additionally builds ``oracle/_ref/miniVite_ref_gpu``: the reference's own ``main.cpp`` with the patch of
+INTEGRATION.md section 2 applied (the ``distLouvainMethod`` call replaced by ``mvgpu_upload_shard`` +
+``mvgpu_louvain`` through the C ABI, everything else -- command line, graph construction, timer brackets, report --
+the reference's code), linked against the shim and ``-lmvgpu``.  ``tests/test_gpu_reference_main.py`` runs it.
+
+Usage: python oracle/build_ref.py [--ref /root/reference] [--force] [--gpu]
 """
 import argparse
 import os
@@ -73,6 +78,68 @@ HOOK_RESULT = r"""      double avgt = (tot_time / nprocs);
 """
 
 
+# ---- INTEGRATION.md section 2, as applied to a throw-away copy of the reference's main.cpp ------------------------------
+GPU_INCLUDE = '#include "mvgpu.h"                       // this repo: include/mvgpu.h ; link with -lmvgpu\n'
+
+GPU_CREATE = r"""  createCommunityMPIType();
+  // one GPU per rank, communicator id via MPI (INTEGRATION.md section 2)
+  unsigned char nccl_id[MVGPU_UNIQUE_ID_BYTES];
+  if (me == 0 && nprocs > 1 && mvgpu_get_unique_id(nccl_id)) { std::cerr << mvgpu_last_error() << std::endl; MPI_Abort(MPI_COMM_WORLD, -99); }
+  MPI_Bcast(nccl_id, sizeof nccl_id, MPI_BYTE, 0, MPI_COMM_WORLD);
+  int ngpu = mvgpu_device_count();
+  mvgpu_ctx *ctx = nullptr;
+  if (ngpu < 1 || mvgpu_create(&ctx, me % ngpu, me, nprocs) || mvgpu_comm_init(ctx, nccl_id)) {
+    std::cerr << mvgpu_last_error() << std::endl; MPI_Abort(MPI_COMM_WORLD, -99);
+  }
+  if (getenv("MV_TRACE")) mvgpu_set_option(ctx, "trace", 1);
+"""
+
+GPU_UPLOAD = r"""  size_t ssz = 0, rsz = 0;
+  std::vector<GraphElem> parts(nprocs + 1);
+  for (int r = 0; r <= nprocs; r++) parts[r] = (r < nprocs) ? g->get_base(r) : g->get_bound(nprocs - 1);
+  if (mvgpu_upload_shard(ctx, g->get_nv(), parts.data(), g->get_lnv(), g->get_lne(),
+                         g->edge_indices_.data(), g->edge_list_.data())) {
+    std::cerr << mvgpu_last_error() << std::endl; MPI_Abort(MPI_COMM_WORLD, -99);
+  }
+"""
+
+GPU_CALL = r"""  if (mvgpu_louvain(ctx, /*lower=*/currMod, threshold, &iters, &currMod)) {
+    std::cerr << mvgpu_last_error() << std::endl; MPI_Abort(MPI_COMM_WORLD, -99);
+  }
+  if (getenv("MV_TRACE") && me == 0) {      // observation hook (same line format as the CPU build's)
+    int n = 0; mvgpu_get_trace(ctx, 0, nullptr, &n);
+    std::vector<mvgpu_iter_trace> tr(n);
+    if (n) mvgpu_get_trace(ctx, n, tr.data(), &n);
+    for (int k = 0; k < n; k++)
+      fprintf(stderr, "ITER %d mod=%.17g moved=%ld chash=%016llx\n", k + 1, tr[k].modularity, (long)tr[k].moved,
+              (unsigned long long)tr[k].chash);
+    double cst = 0; mvgpu_get_constant(ctx, &cst);
+    fprintf(stderr, "FINAL prevMod=%.17g chashCurr=%016llx constant=%.17g\n", currMod,
+            (unsigned long long)(n >= 2 ? tr[n - 2].chash : 0), cst);
+  }
+"""
+
+GPU_DESTROY = "  mvgpu_destroy(ctx);\n  delete g;\n"
+
+REF_CALL = """#if defined(USE_MPI_RMA)
+  currMod = distLouvainMethod(me, nprocs, *g, ssz, rsz, ssizes, rsizes, 
+                svdata, rvdata, currMod, threshold, iters, commwin);
+#else
+  currMod = distLouvainMethod(me, nprocs, *g, ssz, rsz, ssizes, rsizes, 
+                svdata, rvdata, currMod, threshold, iters);
+#endif
+"""
+
+
+def patch_main_for_gpu(m):
+    m = replace_once(m, '#include "dspl.hpp"\n', '#include "dspl.hpp"\n' + GPU_INCLUDE, "mvgpu.h include")
+    m = replace_once(m, "  createCommunityMPIType();\n", GPU_CREATE, "context creation")
+    m = replace_once(m, "  size_t ssz = 0, rsz = 0;\n", GPU_UPLOAD, "shard upload")
+    m = replace_once(m, REF_CALL, GPU_CALL, "distLouvainMethod call")
+    m = replace_once(m, "  delete g;\n", GPU_DESTROY, "context destruction")
+    return m
+
+
 def replace_once(text, old, new, what):
     if text.count(old) != 1:
         raise SystemExit(f"build_ref: anchor for {what!r} found {text.count(old)} times (expected 1)")
@@ -83,8 +150,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--gpu", action="store_true", help="also build miniVite_ref_gpu (reference main.cpp + INTEGRATION.md patch)")
     args = ap.parse_args()
     out_bin = os.path.join(OUT_DIR, "miniVite_ref")
+    gpu_bin = os.path.join(OUT_DIR, "miniVite_ref_gpu")
+    repo = os.path.dirname(HERE)
+    libdir = os.path.join(repo, "minivite_b200", "lib")
     if not os.path.isdir(args.ref):
         if os.path.exists(out_bin):
             print(f"build_ref: {args.ref} absent; keeping prebuilt {out_bin}")
@@ -93,7 +164,11 @@ def main():
         return 1
     srcs = [os.path.join(args.ref, f) for f in ("main.cpp", "dspl.hpp", "graph.hpp", "utils.hpp")]
     stamp = max(os.path.getmtime(p) for p in srcs + [__file__, os.path.join(SHIM_DIR, "mpi.h")])
-    if not args.force and os.path.exists(out_bin) and os.path.getmtime(out_bin) >= stamp:
+    want_gpu = args.gpu and os.path.exists(os.path.join(libdir, "libmvgpu.so"))
+    gpu_stamp = max(stamp, os.path.getmtime(os.path.join(repo, "include", "mvgpu.h")))
+    cpu_fresh = os.path.exists(out_bin) and os.path.getmtime(out_bin) >= stamp
+    gpu_fresh = not want_gpu or (os.path.exists(gpu_bin) and os.path.getmtime(gpu_bin) >= gpu_stamp)
+    if not args.force and cpu_fresh and gpu_fresh:
         print(f"build_ref: {out_bin} up to date")
         return 0
     os.makedirs(OUT_DIR, exist_ok=True)
@@ -117,6 +192,13 @@ def main():
                "-I", SHIM_DIR, "-I", tmp, os.path.join(tmp, "main.cpp"), "-o", out_bin]
         print("build_ref:", " ".join(cmd))
         subprocess.check_call(cmd)
+        if want_gpu:
+            open(os.path.join(tmp, "main_gpu.cpp"), "w").write(patch_main_for_gpu(m))
+            cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-DPRINT_DIST_STATS",
+                   "-I", SHIM_DIR, "-I", tmp, "-I", os.path.join(repo, "include"), os.path.join(tmp, "main_gpu.cpp"),
+                   "-o", gpu_bin, "-L", libdir, "-lmvgpu", "-Wl,-rpath,$ORIGIN/../../minivite_b200/lib"]
+            print("build_ref:", " ".join(cmd))
+            subprocess.check_call(cmd)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     print(f"build_ref: wrote {out_bin}")

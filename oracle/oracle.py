@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "louvain_oracle.c")
 LIB = os.path.join(HERE, "_build", "liblouvain_oracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "miniVite_ref")
+REF_GPU_BIN = os.path.join(HERE, "_ref", "miniVite_ref_gpu")   # reference main.cpp + INTEGRATION.md patch (build_ref.py --gpu)
 
 TRACE_DTYPE = np.dtype([("modularity", "<f8"), ("moved", "<i8"), ("chash", "<u8")])
 EDGE_DTYPE = np.dtype([("tail", "<i8"), ("weight", "<f8")])
@@ -98,12 +99,14 @@ _RESULT_RE = re.compile(r"RESULT mod=(\S+) iters=(\d+) time=(\S+) nv=(\d+) ne=(\
 
 
 def run_reference(args, nranks=1, threads=1, trace=True, dump_comm=None, dump_graph=None, cwd=None, timeout=None,
-                  arena_gb=None):
+                  arena_gb=None, binary=None, extra_env=None):
     """Run oracle/_ref/miniVite_ref with the reference's own command line (`args`, e.g. ["-n","16384"] or
     ["-f", path]); `nranks` processes (fork shim) x `threads` OpenMP threads.  Returns parsed results."""
-    if not have_reference():
-        raise RuntimeError("oracle/_ref/miniVite_ref missing (run oracle/build_ref.py where /root/reference exists)")
+    binary = binary or REF_BIN
+    if not (os.path.exists(binary) and os.access(binary, os.X_OK)):
+        raise RuntimeError(f"{binary} missing (run oracle/build_ref.py where /root/reference exists)")
     env = dict(os.environ, MVSHIM_NP=str(nranks), OMP_NUM_THREADS=str(threads))
+    env.update(extra_env or {})
     env.pop("MV_TRACE", None)
     if trace:
         env["MV_TRACE"] = "1"
@@ -113,7 +116,7 @@ def run_reference(args, nranks=1, threads=1, trace=True, dump_comm=None, dump_gr
         env["MV_DUMP_GRAPH"] = dump_graph
     if arena_gb:
         env["MVSHIM_ARENA_GB"] = str(arena_gb)
-    p = subprocess.run([REF_BIN] + [str(a) for a in args], env=env, capture_output=True, text=True, cwd=cwd,
+    p = subprocess.run([binary] + [str(a) for a in args], env=env, capture_output=True, text=True, cwd=cwd,
                        timeout=timeout)
     if p.returncode != 0:
         raise RuntimeError(f"reference failed rc={p.returncode}: {p.stderr[-2000:]}")

@@ -172,13 +172,14 @@ def test_scan_variants_agree(gpu, golden):
     nv, parts, rowptr, edges = as_single(case)
     for opts in ({"scan_variant": 0}, {"scan_variant": 0, "cache_policy": 0}, {"scan_variant": 3, "cache_policy": 0},
                  {"scan_variant": 3}, {"scan_variant": 3, "reorder": 1}, {"scan_variant": 3, "force_weighted": 1},
+                 {"scan_variant": 4}, {"scan_variant": 4, "reorder": 1}, {"scan_variant": 4, "force_weighted": 1},
                  {"scan_variant": 3, "force_heavy_deg": 8, "reorder": 1}, {"scan_variant": 0, "force_weighted": 1, "reorder": 1}):
         res = run_single(gpu, parts, rowptr, edges, nv, **opts)
         assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
     for name in ("hand_weighted20_p1", "rgg_n16384_p1_w", "hand_loops_multi_p1", "hand_star41_p1", "hand_k66_p1"):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
-        for var in (0, 3):
+        for var in (0, 3, 4):
             res = run_single(gpu, parts, rowptr, edges, nv, scan_variant=var)
             assert abs(res["modularity"] - float(case["modularity"])) <= 1e-6 and res["iters"] == case["iters"], (name, var)
 
