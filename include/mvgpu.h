@@ -102,16 +102,19 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
 /* Options: "trace" (0/1: record moved/chash per iteration, default 0), "max_iters" (safety cap,
  * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
- * "scan_variant" (3 = warp-synchronous loops (default), 0 = first kernel; identical results),
- * "cache_policy" (bit2 = L2 evict_first hint on the streamed arrays of the default scan kernel; other bits are
- * accepted and ignored; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
+ * "scan_variant" (4 = k_scan_pw: persistent warps fed by TMA bulk copies (default); 3 = k_scan_ws: one CTA per
+ * 128-vertex tile, the default of round 1; identical results), "first_iter" (1 (default): iteration 1 of a simple
+ * unit-weight graph uses the singleton-community reduction of k_scan_pw; 0: the general reduction; identical results),
+ * "cache_policy" (bit2 = L2 evict_first hint on the streamed arrays of k_scan_ws; other bits are accepted and
+ * ignored; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
- * vertices per BFS region of the renumbering, default 512), "degree_sort" (experimental layout refinement of the
- * renumbering: vertices ordered by degree inside windows of 256 / 512 / 1024 / 2048 positions; 0 (default) = off), "fold_variant" (experimental: 1 = unit-weight fold
- * with 16-byte accesses; 0 (default)), "comm_mode" (multi-GPU per-iteration exchanges: 1 = stores /
- * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "compact_upload" (1:
+ * vertices per BFS region of the renumbering, default 512), "comm_mode" (multi-GPU per-iteration exchanges: 1 = stores /
+ * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "host_transport" (set before
+ * mvgpu_comm_init; 1: the setup-time exchanges go through a shared-memory segment of the host instead of NCCL --
+ * required when several ranks share one device, which NCCL refuses; needs comm_mode 1; default 0), "compact_upload" (1:
  * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 0 (default) = the 16-byte
- * records as they are), "host_threads" (threads of that host pass, default 8). */
+ * records as they are), "host_threads" (threads of that host pass, default 8).
+ * The environment variable MVGPU_OPTIONS="name=value,name=value" presets options for every context of the process. */
 /* In a multi-rank run every rank must set the same options (they change which collectives a run issues). */
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);
 int mvgpu_get_trace(mvgpu_ctx *ctx, int max_entries, mvgpu_iter_trace *out, int *n);

@@ -239,201 +239,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// ----------------------------------------------------------------------------------------------
-// The neighbour-scan kernel: distExecuteLouvainIteration + distBuildLocalMapCounter +
-// distGetMaxIndex (dspl.hpp:276-405, 230-274, 174-228) for every vertex of the shard.
-//
-// One CTA owns a tile of kTileV (128) consecutive vertices; their CSR edges are one contiguous range.
-//   phase A (edge-parallel, all lanes busy, coalesced): stream the int32 tails of the tile,
-//           gather cur[tail] (the only random access per edge; 4 B from an L2-resident array) and
-//           stage the neighbour communities (and weights) in shared memory;
-//   phase B (vertex-parallel): each thread reduces its vertex's staged segment to
-//           (community, weight-sum) pairs in place -- sums in edge order, like counter[] in the
-//           reference --, gathers Comm{size,degree} once per distinct community, evaluates dQ with
-//           the reference's exact fp64 rounding sequence, applies the tie-break and the singleton
-//           veto, writes targetComm and pushes the +/- deltas with one (unit) or two (weighted)
-//           atomics per touched community (local HBM or the owner GPU's memory over NVLink).
-// Tiles with more than kECap edges are processed in several sub-ranges; vertices with more than
-// heavy_deg edges are skipped here and handled by k_scan_heavy.
-// ----------------------------------------------------------------------------------------------
-template <bool UNIT, bool MULTI, bool TRACE>
-__global__ void __launch_bounds__(kTileV) k_scan(const ScanParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *s_comm = reinterpret_cast<int32_t *>(smem_raw);                       // kECap
-  int32_t *s_cnt = s_comm + kECap;                                               // unit: kECap counts
-  double *s_w = reinterpret_cast<double *>(smem_raw + sizeof(int32_t) * kECap);  // weighted: kECap sums
-  __shared__ int s_next;
-  __shared__ unsigned long long s_red[3][kTileV / 32];
-  __shared__ double s_redd[kTileV / 32];
-
-  const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * kTileV;
-  const int v1 = min(p.lnv, v0 + kTileV);
-  const int v = v0 + tid;
-  uint32_t r0 = 0, r1 = 0;
-  if (v < v1) { r0 = p.rowptr[v]; r1 = p.rowptr[v + 1]; }
-  const uint32_t deg = r1 - r0;
-  const bool is_heavy = deg > (uint32_t)p.heavy_deg;
-
-  unsigned long long acc_le_u = 0, acc_moved = 0, acc_hash = 0;
-  double acc_le_d = 0.0;
-
-  int start = v0;
-  while (start < v1) {
-    // ---- choose the sub-range [start, end): longest run of non-heavy vertices whose edges fit the buffer
-    __shared__ uint32_t s_e0;
-    __shared__ int s_skip, s_end;
-    if (tid == start - v0) { s_e0 = r0; s_skip = is_heavy ? 1 : 0; s_end = v1; }
-    __syncthreads();
-    if (s_skip) { start++; __syncthreads(); continue; }
-    const uint32_t E0 = s_e0;
-    if (v > start && v < v1 && (is_heavy || (r1 - E0 > (uint32_t)kECap))) atomicMin(&s_end, v);
-    __syncthreads();
-    const int end = s_end;                         // > start: the start vertex itself always fits
-    if (tid == end - 1 - v0) s_next = (int)r1;     // last vertex of the sub-range publishes E1
-    __syncthreads();
-    const uint32_t E1 = (uint32_t)s_next;
-    const int ne = (int)(E1 - E0);
-
-    // ---- phase A: stage neighbour communities (and weights)
-    {
-      const int32_t *tl = p.tails + E0;
-      int i = tid;
-      for (; i + 3 * kTileV < ne; i += 4 * kTileV) {
-        const int t0 = ld_stream(tl + i), t1 = ld_stream(tl + i + kTileV), t2 = ld_stream(tl + i + 2 * kTileV),
-                  t3 = ld_stream(tl + i + 3 * kTileV);
-        const int c0 = __ldg(p.cur + t0), c1 = __ldg(p.cur + t1), c2 = __ldg(p.cur + t2), c3 = __ldg(p.cur + t3);
-        s_comm[i] = c0; s_comm[i + kTileV] = c1; s_comm[i + 2 * kTileV] = c2; s_comm[i + 3 * kTileV] = c3;
-      }
-      for (; i < ne; i += kTileV) s_comm[i] = __ldg(p.cur + ld_stream(tl + i));
-      if (!UNIT) {
-        const double *wl = p.weights + E0;
-        for (int k = tid; k < ne; k += kTileV) s_w[k] = ld_stream(wl + k);
-      }
-    }
-    __syncthreads();
-
-    // ---- phase B: one thread per vertex of the sub-range
-    if (v >= start && v < end) {
-      const int cc = __ldg(p.cur + v);
-      int best = cc;
-      if (deg != 0) {
-        const int o0 = (int)(r0 - E0);
-        const int d = (int)deg;
-        int nd = 0;
-        // own-community Comm{size,degree}
-        int owner; long long idx;
-        locate_impl<MULTI>(p.pt, p.base, p.lnv, cc, owner, idx);
-        double vdeg, eix, ax, cc_deg; long long cc_size;
-        if (UNIT) {
-          int cnt0 = 0;
-          for (int k = 0; k < d; k++) {
-            const int ck = s_comm[o0 + k];
-            if (ck == cc) { cnt0++; continue; }
-            if (ck < 0) continue;
-            int c = 1;
-            for (int j = k + 1; j < d; j++)
-              if (s_comm[o0 + j] == ck) { c++; s_comm[o0 + j] = -1; }
-            s_comm[o0 + nd] = ck; s_cnt[o0 + nd] = c; nd++;
-          }
-          cc_size = (long long)__ldg(ptr_csize<MULTI>(p, owner) + idx);
-          cc_deg = (double)__ldg(ptr_cdeg<MULTI>(p, owner) + idx);
-          vdeg = (double)d;
-          const int sl = p.has_self ? __ldg(p.self_i + v) : 0;
-          eix = (double)(cnt0 - sl);
-          acc_le_u += (unsigned long long)cnt0;
-        } else {
-          double w0 = 0.0;                                   // counter[0] starts at 0.0 (dspl.hpp:313)
-          for (int k = 0; k < d; k++) {
-            const int ck = s_comm[o0 + k];
-            if (ck == cc) { w0 += s_w[o0 + k]; continue; }
-            if (ck < 0) continue;
-            double sum = s_w[o0 + k];
-            for (int j = k + 1; j < d; j++)
-              if (s_comm[o0 + j] == ck) { sum += s_w[o0 + j]; s_comm[o0 + j] = -1; }
-            s_comm[o0 + nd] = ck; s_w[o0 + nd] = sum; nd++;
-          }
-          const CommW *cw = ptr_cinfo_w<MULTI>(p, owner) + idx;
-          const double2 raw = __ldg(reinterpret_cast<const double2 *>(cw));
-          cc_size = __double_as_longlong(raw.x);
-          cc_deg = raw.y;
-          vdeg = __ldg(p.vdeg + v);
-          const double sl = p.has_self ? __ldg(p.self_d + v) : 0.0;
-          eix = __dsub_rn(w0, sl);
-          acc_le_d += w0;
-        }
-        ax = __dsub_rn(cc_deg, vdeg);
-        double best_gain = 0.0;
-        long long best_size = cc_size;
-        int lbest = kNoLabel;
-        for (int m = 0; m < nd; m++) {
-          const int y = s_comm[o0 + m];
-          int yo; long long yi;
-          locate_impl<MULTI>(p.pt, p.base, p.lnv, y, yo, yi);
-          double ay, eiy; long long ysize;
-          if (UNIT) {
-            ysize = (long long)__ldg(ptr_csize<MULTI>(p, yo) + yi);
-            ay = (double)__ldg(ptr_cdeg<MULTI>(p, yo) + yi);
-            eiy = (double)s_cnt[o0 + m];
-          } else {
-            const double2 raw = __ldg(reinterpret_cast<const double2 *>(ptr_cinfo_w<MULTI>(p, yo) + yi));
-            ysize = __double_as_longlong(raw.x);
-            ay = raw.y;
-            eiy = s_w[o0 + m];
-          }
-          const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
-          if (better_l<MULTI>(p, g, y, best_gain, best, lbest)) { best_gain = g; best = y; best_size = ysize; }
-        }
-        if (best_size == 1 && cc_size == 1 && label_greater<MULTI>(p, best, lbest, cc)) best = cc;   // dspl.hpp:224-225
-        if (best != cc) {                                                    // dspl.hpp:331-399
-          int bo; long long bi;
-          locate_impl<MULTI>(p.pt, p.base, p.lnv, best, bo, bi);
-          if (UNIT) {
-            atomicAdd(ptr_upd<MULTI>(p, bo) + bi, pack_delta(1, (long long)d));
-            atomicAdd(ptr_upd<MULTI>(p, owner) + idx, pack_delta(-1, -(long long)d));
-          } else {
-            atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, bo) + bi), 1ULL);
-            atomicAdd(ptr_udeg<MULTI>(p, bo) + bi, vdeg);
-            atomicAdd((unsigned long long *)(ptr_usize<MULTI>(p, owner) + idx), ~0ULL);
-            atomicAdd(ptr_udeg<MULTI>(p, owner) + idx, -vdeg);
-          }
-        }
-      }
-      p.tgt[v] = best;                                                       // dspl.hpp:404
-      if (TRACE) { acc_moved += (best != cc); acc_hash += vhash(label_of<MULTI>(p, (int)(p.base + v)), label_of<MULTI>(p, best)); }
-    }
-    start = end;
-    __syncthreads();
-  }
-
-  // ---- CTA reduction of the modularity / trace partial sums, one atomic each per CTA
-  const int lane = tid & 31, wid = tid >> 5;
-  if (UNIT) { const unsigned long long s = warp_sum(acc_le_u); if (lane == 0) s_red[0][wid] = s; }
-  else { const double s = warp_sum(acc_le_d); if (lane == 0) s_redd[wid] = s; }
-  if (TRACE) {
-    const unsigned long long a = warp_sum(acc_moved), b = warp_sum(acc_hash);
-    if (lane == 0) { s_red[1][wid] = a; s_red[2][wid] = b; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    if (UNIT) {
-      unsigned long long s = 0;
-      for (int w = 0; w < kTileV / 32; w++) s += s_red[0][w];
-      if (s) atomicAdd(&p.acc->le_u, s);
-    } else {
-      double s = 0;
-      for (int w = 0; w < kTileV / 32; w++) s += s_redd[w];
-      if (s != 0.0) atomicAdd(&p.acc->le_d, s);
-    }
-    if (TRACE) {
-      unsigned long long a = 0, b = 0;
-      for (int w = 0; w < kTileV / 32; w++) { a += s_red[1][w]; b += s_red[2][w]; }
-      atomicAdd(&p.acc->moved, a);
-      atomicAdd(&p.acc->hash, b);
-    }
-  }
-}
-
 // ---- helpers shared by the scan kernels ----------------------------------------------------------------
 template <bool MULTI>
 __device__ __forceinline__ void push_move_unit(const ScanParams &p, int cc, int best, int d) {
@@ -450,9 +255,14 @@ __device__ __forceinline__ void push_move_w(const ScanParams &p, int cc, int bes
 }
 
 // ----------------------------------------------------------------------------------------------
-// Scan kernel, second generation ("warp-synchronous loops"), the default.  Same tiles and phase A as k_scan.  Profiling k_scan
-// once the layout had locality showed it issue-bound at 12 of 32 lanes active: in the in-place reduction every
-// lane starts its inner "count this community" loop at a different moment, so the warp serialises them.  Here
+// Neighbour-scan kernel, second generation ("warp-synchronous loops"; option scan_variant=3, the default of round 1;
+// the default is now k_scan_pw in scan_pipe.cuh, which keeps this kernel's phase B):
+// distExecuteLouvainIteration + distBuildLocalMapCounter + distGetMaxIndex (dspl.hpp:276-405, 230-274, 174-228).
+// One CTA owns a tile of kTileV (128) consecutive vertices; their CSR edges are one contiguous range.
+//   phase A (edge-parallel, all lanes busy, coalesced): stream the int32 tails of the tile, gather cur[tail] (the only
+//           random access per edge) and stage the neighbour communities (and weights) in shared memory;
+//   phase B (vertex-parallel): the first kernel of round 1 let every lane run its own "count this community" loop and
+//           was issue-bound at 12 of 32 lanes active, because the warp serialised them.  Here
 // phase B is arranged so that the lanes of a warp run the same loop at the same time:
 //   pass 0   counter[0] = weight towards the own community (one uniform walk over the staged segment); the other
 //            neighbours are compacted to the front of the segment;
@@ -1048,43 +858,54 @@ __global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *
 #ifndef MV_BFS_SUB
 #define MV_BFS_SUB 4
 #endif
-#ifndef MV_BFS_DONE
-#define MV_BFS_DONE 0      // 0: keys only; 1: `done` bitmap lets the level sweep skip settled vertices; 2: it also filters the edge probes
+#ifndef MV_BFS_LVL8
+#define MV_BFS_LVL8 1      // byte-per-vertex level array in front of the keys (see k_msbfs)
 #endif
 constexpr unsigned int kBfsRegionBits = 22;
 constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
-                                               int region_stride, int max_levels, unsigned int *level_flags, uint32_t *done) {
+                                               int region_stride, int max_levels, unsigned int *level_flags, uint8_t *lvl8) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  for (int v = gtid; v < lnv; v += gsz)
-    key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
-  for (int w = gtid; w < (lnv + 31) / 32; w += gsz) done[w] = 0;
+  for (int v = gtid; v < lnv; v += gsz) {
+    const bool seed = v % region_stride == 0;
+    key[v] = seed ? (unsigned int)(v / region_stride) : kBfsUnreached;
+    lvl8[v] = seed ? 0 : 255;
+  }
   grid.sync();
   const int lane = threadIdx.x & 31;
-  // `done` (compile-time option MV_BFS_DONE, off: measured slower at config 2, profiles/README.md round 2): one bit per
-  // vertex, set when the vertex has been expanded.  1: a warp skips the key load of 32 settled vertices in the level
-  // sweep; 2: an edge probe whose target is settled also skips the random key[] sector.  Keys still decide.
-  // Frontier vertices found by a warp are parked in shared memory and expanded MV_BFS_SUB at a time, 32 / MV_BFS_SUB lanes each,
-  // so that several adjacency reads and their dependent probes are in flight per warp.
+  // lvl8[v] = BFS level of v (255: not reached yet), one BYTE per vertex next to the 4-byte keys (MV_BFS_LVL8, default on).
+  // The keys alone cost one random 32-byte DRAM sector per edge probe -- 6.4 GB per run at config 2, nearly all of it for
+  // targets that were settled levels ago (profiles/r2_msbfs_sub4_summary.md) -- and one 67 MB sweep per level.  The byte
+  // array is a quarter of that, stays in L2, and answers both questions: the level sweep reads it instead of the
+  // keys, and a probe goes on to the key only if the target is not known to sit at a level <= the current one.  A
+  // stale 255 only costs the probe the filter would have saved; the keys (atomicMin on level<<22|region) still decide,
+  // so the result is the same deterministic minimum as before.
+  // Frontier vertices found by a warp are parked in shared memory and expanded MV_BFS_SUB at a time, 32 / MV_BFS_SUB lanes
+  // each, so that several adjacency reads and their dependent probes are in flight per warp.
   constexpr int kBfsSub = MV_BFS_SUB, kBfsLanes = 32 / kBfsSub;
   __shared__ uint32_t s_front[256 / 32][32][3];
   uint32_t(*front)[3] = s_front[threadIdx.x >> 5];
   for (int level = 0; level < max_levels; level++) {
     bool any = false;
-    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {          // vb is a multiple of 32: one `done` word per warp step
-      const uint32_t dw = MV_BFS_DONE ? __ldcg(done + (vb >> 5)) : 0u;
-      if (dw == 0xffffffffu) continue;
+    const bool bytes = MV_BFS_LVL8 && level < 254;              // deeper searches fall back to the keys
+    const unsigned char next8 = (unsigned char)(level + 1);
+    for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
       const int v = vb + lane;
+      bool active = false;
       unsigned int k = kBfsUnreached;
-      if (v < lnv && !((dw >> lane) & 1u)) k = __ldcg(key + v);
-      const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
+      if (bytes) {
+        active = v < lnv && __ldcg(lvl8 + v) == (unsigned char)level;
+        if (active) k = __ldcg(key + v);
+      } else {
+        if (v < lnv) k = __ldcg(key + v);
+        active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
+      }
       const unsigned int m = __ballot_sync(0xffffffffu, active);
       if (m == 0) continue;
       any = true;
-      if (MV_BFS_DONE && lane == 0) __stcg(done + (vb >> 5), dw | m);
       if (active) {
         const int slot = __popc(m & ((1u << lane) - 1u));
         front[slot][0] = ((unsigned int)(level + 1) << kBfsRegionBits) | (k & ((1u << kBfsRegionBits) - 1));
@@ -1098,7 +919,11 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
         const uint32_t e1 = front[i][2];
         for (uint32_t e = front[i][1] + (lane % kBfsLanes); e < e1; e += kBfsLanes) {
           const int w = tails[e];
-          if (w < lnv && (MV_BFS_DONE < 2 || !((__ldcg(done + (w >> 5)) >> (w & 31)) & 1u)) && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
+          if (w >= lnv) continue;
+          if (bytes) {
+            if (__ldcg(lvl8 + w) <= (unsigned char)level) continue;       // settled at this level or before: its key is smaller
+            if (__ldcg(key + w) > nk) { atomicMin(&key[w], nk); lvl8[w] = next8; }
+          } else if (__ldcg(key + w) > nk) atomicMin(&key[w], nk);
         }
       }
       __syncwarp();

@@ -174,7 +174,7 @@ struct mvgpu_ctx {
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned last_gens[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 3, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 4, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -394,7 +394,6 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp, bool first) {
   const size_t smem = UNIT ? sizeof(int32_t) * 2 * kECap : sizeof(int32_t) * kECap + sizeof(double) * kECap;
   static bool attr_done = false;
   if (!attr_done) {
-    CK(cudaFuncSetAttribute(k_scan<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k_scan_ws<UNIT, MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
@@ -414,8 +413,7 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp, bool first) {
     else k_scan_pw<UNIT, MULTI, TRACE, false><<<grid, kPwWarps * 32, pw_smem_bytes<UNIT>(), c->stream>>>(sp, ngroups);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   } else if (tiles > 0) {
-    if (c->opt_scan_variant == 0) k_scan<UNIT, MULTI, TRACE><<<tiles, kTileV, smem, c->stream>>>(sp);
-    else k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
+    k_scan_ws<UNIT, MULTI, TRACE><<<tiles, kTileV, UNIT ? sizeof(int32_t) * kECap : smem, c->stream>>>(sp);
     c->tm.kernel_launches++; c->tm.scan_launches++;
   }
   if (c->nheavy > 0) {
@@ -638,10 +636,10 @@ int setup_run(mvgpu_ctx *c) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msbfs, 256, 0));
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
-        TRY(c->bfs_visited.ensure((size_t)(lnv + 31) / 32 + 1));
+        TRY(c->bfs_visited.ensure((size_t)(lnv + 3) / 4 + 1));      // one byte per vertex
         const uint32_t *rp = src_rowptr; const int32_t *tl = src_tails; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        uint32_t *done = c->bfs_visited.p;
-        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf, &done};
+        uint8_t *lvl8 = reinterpret_cast<uint8_t *>(c->bfs_visited.p);
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf, &lvl8};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
         // sort by (region, level): only the bits that can be set take part (one radix pass less than a 32-bit sort)
         const long long nregions = (lnv + stride - 1) / stride;
@@ -1320,7 +1318,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
   else if (n == "force_weighted") c->opt_force_weighted = value != 0;
   else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
-  else if (n == "scan_variant") c->opt_scan_variant = (int)value;
+  else if (n == "scan_variant") { if (value != 3 && value != 4) return fail("scan_variant must be 4 (k_scan_pw, default) or 3 (k_scan_ws)"); c->opt_scan_variant = (int)value; }
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else if (n == "reorder") c->opt_reorder = (int)value;
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;

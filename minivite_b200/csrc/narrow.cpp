@@ -2,8 +2,10 @@
 // 16-byte Edge records {int64 tail; double weight} (graph.hpp:60-66) to 4-byte tails, checking on the way that
 // every weight is exactly 1.0 and every tail lies in [0, nv), and counting the tails outside [base, bound).
 // Plain C++ (no CUDA): compiled by g++ and linked into libmvgpu.so.  An AVX2 body is picked at run time when the
-// CPU has it (the generic x86-64 baseline only vectorises this loop poorly: ~4 GB/s per core).
+// CPU has it (the generic x86-64 baseline only vectorises this loop poorly: ~4 GB/s per core).  An AVX-512 body with
+// non-temporal stores was measured on the GPU box in round 2 and lost (upload 31 -> 44 ms at 16 threads): removed.
 #include <stdint.h>
+#include <stdlib.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -55,6 +57,7 @@ __attribute__((target("avx2"))) void narrow_avx2(const Rec *src, long long n, lo
   if (_mm256_movemask_epi8(okw) != -1 || !_mm256_testz_si256(badr, badr)) bad |= 1;
   if (e < n) narrow_scalar(src + e, n - e, nv, base, bound, dst + e, nrem, bad);
 }
+
 #endif
 
 }  // namespace

@@ -23,7 +23,7 @@
 namespace mv {
 
 #ifndef MV_WCAP_UNIT
-#define MV_WCAP_UNIT 448
+#define MV_WCAP_UNIT 512
 #endif
 #ifndef MV_WCAP_W
 #define MV_WCAP_W 320

@@ -7,6 +7,14 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# Ranks that are THREADS of one process (tests/test_gpu_multirank_one_device.py) synchronise through kernels that
+# spin on flags written by a peer's kernel.  CUDA's default lazy module loading takes a context-wide lock the first
+# time a kernel is launched, which a spinning peer kernel would block forever; eager loading (read once, when the
+# process initialises CUDA) removes that first-launch dependency.  Ranks in separate processes are not affected.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+# ... and with 8 such ranks their streams must not be multiplexed onto the default 8 hardware queues: a kernel queued
+# behind a peer's spinning barrier kernel would never start
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def pytest_configure(config):
@@ -16,6 +24,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "ref_traces.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.fixture(scope="session")
+def golden_rmat():
+    """Reference traces on power-law graphs (tests/golden/make_golden_rmat.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "rmat_traces.json")) as f:
         return json.load(f)["cases"]
 
 

@@ -29,6 +29,14 @@ def case_graph(case):
             rps.append(np.ascontiguousarray(sh.rowptr[a:b + 1] - sh.rowptr[a]))
             eds.append(np.ascontiguousarray(sh.edges[sh.rowptr[a]:sh.rowptr[b]]))
         return parts, rps, eds, ss
+    if kind == "rmat":
+        n, rowptr, edges = rmat_graph(case["scale"], case["edge_factor"], case["seed"])
+        if case.get("balanced"):
+            parts = np.array(case["parts"], dtype=np.int64)     # the reference's own -b bins (graph.hpp:466-572)
+            rps = [np.ascontiguousarray(rowptr[a:b + 1] - rowptr[a]) for a, b in zip(parts[:-1], parts[1:])]
+            eds = [np.ascontiguousarray(edges[rowptr[a]:rowptr[b]]) for a, b in zip(parts[:-1], parts[1:])]
+            return parts, rps, eds, None
+        return split_global(n, rowptr, edges, p) + (None,)
     if kind == "hand":
         g = case["graph"]
         edges = np.zeros(len(g["tails"]), hg.EDGE_DTYPE)
@@ -71,3 +79,35 @@ def assert_trace_matches(case, iters, modularity, trace, final_chash=None, comm=
         assert final_chash == int(case["final_chash"], 16)
     if comm is not None and "comm" in case and exact:
         assert [int(x) for x in comm] == case["comm"]
+
+
+def rmat_graph(scale, edge_factor, seed, a=0.57, b=0.19, c=0.19):
+    """Power-law (R-MAT) graph in the reference's CSR format: symmetric, unit weights, no self loops, no parallel
+    edges, adjacency sorted by tail.  numpy's legacy RandomState keeps the stream stable across versions, so the graph
+    is a function of (scale, edge_factor, seed) and only its golden TRACE needs committing."""
+    rng = np.random.RandomState(seed)
+    n, m = 1 << scale, edge_factor << scale
+    src = np.zeros(m, np.int64)
+    dst = np.zeros(m, np.int64)
+    for level in range(scale):
+        r = rng.random_sample(m)
+        right = (r >= a) & (r < a + b) | (r >= a + b + c)          # quadrants b and d set the column bit
+        down = r >= a + b                                          # quadrants c and d set the row bit
+        src |= down.astype(np.int64) << level
+        dst |= right.astype(np.int64) << level
+    perm = rng.permutation(n)                                      # scatter the hubs over the id range
+    src, dst = perm[src], perm[dst]
+    keep = src != dst
+    lo, hi = np.minimum(src[keep], dst[keep]), np.maximum(src[keep], dst[keep])
+    key = np.unique(lo * n + hi)
+    lo, hi = key // n, key % n
+    s2, d2 = np.concatenate([lo, hi]), np.concatenate([hi, lo])
+    order = np.lexsort((d2, s2))
+    s2, d2 = s2[order], d2[order]
+    rowptr = np.zeros(n + 1, np.int64)
+    np.add.at(rowptr, s2 + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    edges = np.zeros(len(d2), hg.EDGE_DTYPE)
+    edges["tail"] = d2
+    edges["weight"] = 1.0
+    return n, rowptr, edges

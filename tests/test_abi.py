@@ -85,3 +85,36 @@ def test_compact_upload_host_pass():
             f[field][pos] = val
             assert run(f, 37, 0, 37)[2] == 1, (pos, field, val)
     assert run(e, 37, 0, 37)[1:] == (0, 0)
+
+
+def test_narrow_edges_host_pass_matches_numpy():
+    """mv_narrow_edges (host half of the compact upload; AVX-512 / AVX2 / scalar bodies picked at run time): tails,
+    remote count and the validation flag against a numpy restatement, on ragged lengths and misaligned outputs."""
+    import ctypes
+    import numpy as np
+    from minivite_b200 import gpu as G
+    L = G.lib()
+    L.mv_narrow_edges.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                  ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_int)]
+    L.mv_narrow_edges.restype = None
+    rng = np.random.default_rng(5)
+    nv, base, bound = 1 << 20, 300000, 700000
+    for n in (0, 1, 7, 8, 9, 63, 1000, 4099):
+        for off in (0, 1, 3):
+            rec = np.zeros(n, np.dtype([("tail", "<i8"), ("weight", "<f8")]))
+            rec["tail"] = rng.integers(0, nv, n)
+            rec["weight"] = 1.0
+            buf = np.zeros(n + 16, np.int32)
+            dst = buf[off:off + n]
+            nrem, bad = ctypes.c_longlong(0), ctypes.c_int(0)
+            L.mv_narrow_edges(rec.ctypes.data, n, nv, base, bound, dst.ctypes.data, ctypes.byref(nrem), ctypes.byref(bad))
+            assert bad.value == 0 and np.array_equal(dst, rec["tail"].astype(np.int32))
+            assert nrem.value == int(((rec["tail"] < base) | (rec["tail"] >= bound)).sum())
+            assert buf[:off].sum() == 0 and buf[off + n:].sum() == 0
+            if n:
+                for field, val in (("weight", 2.0), ("tail", -1), ("tail", nv)):
+                    r2 = rec.copy()
+                    r2[field][n // 2] = val
+                    bad = ctypes.c_int(0)
+                    L.mv_narrow_edges(r2.ctypes.data, n, nv, base, bound, dst.ctypes.data, ctypes.byref(nrem), ctypes.byref(bad))
+                    assert bad.value == 1, (n, field, val)

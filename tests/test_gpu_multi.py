@@ -109,7 +109,7 @@ def test_multi_gpu_with_renumbering(tmp_path, golden):
         res = run_ranks(tmp_path, 2, name, reorder=1, region_size=64)
         assert res["timings"]["reordered"] == 1
         check(res, golden[name])
-    res = run_ranks(tmp_path, 2, "rgg_n16384_p2", reorder=1, region_size=64, scan_variant=0)
+    res = run_ranks(tmp_path, 2, "rgg_n16384_p2", reorder=1, region_size=64, scan_variant=3)
     check(res, golden["rgg_n16384_p2"])
 
 

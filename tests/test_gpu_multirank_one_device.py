@@ -127,3 +127,18 @@ def test_rank_processes_sharing_one_device(tmp_path, golden):
     res = json.load(open(tmp_path / "res.json"))
     trace = [{"modularity": float(m), "moved": mv, "chash": h} for m, mv, h in res["trace"]]
     assert_trace_matches(golden["rgg_n16384_p2"], res["iters"], float(res["mod"]), trace, None, res["comm"])
+
+
+def run_threads_case(case, **opts):
+    """like run_threads, for a case dictionary that is not in ref_traces.json"""
+    return run_threads({"_": case}, "_", case["nranks"], **opts)
+
+
+@pytest.mark.parametrize("name", ["rmat_s14_p2", "rmat_s14_p2_b", "rmat_s17_p4_b"])
+def test_power_law_graph_ranks_on_one_device(golden_rmat, name):
+    """`-f` R-MAT graph on 2 / 4 ranks, plain and edge-balanced (-b) partitions: hubs whose neighbours live on other
+    ranks go through the high-degree kernel with remote community reads."""
+    case = golden_rmat[name]
+    res = run_threads_case(case)
+    assert_trace_matches(case, res["iters"], res["mod"], res["trace"], None, None)
+    assert sum(i["nheavy"] for i in res["info"]) > 0

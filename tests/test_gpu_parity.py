@@ -166,22 +166,26 @@ def test_one_call_seam(gpu, golden):
 
 
 def test_scan_variants_agree(gpu, golden):
-    """generic kernel (scan_variant=0) and register/sorting-network kernel (1) give the same golden trace;
-    cache-policy settings never change results."""
+    """k_scan_pw (4, default) and k_scan_ws (3) give the same golden trace; cache-policy settings never change results.
+    (tests/test_gpu_scan_kernels.py runs every golden case and the unusual graphs through both.)"""
     case = golden["rgg_n65536_p1"]
     nv, parts, rowptr, edges = as_single(case)
-    for opts in ({"scan_variant": 0}, {"scan_variant": 0, "cache_policy": 0}, {"scan_variant": 3, "cache_policy": 0},
-                 {"scan_variant": 3}, {"scan_variant": 3, "reorder": 1}, {"scan_variant": 3, "force_weighted": 1},
-                 {"scan_variant": 4}, {"scan_variant": 4, "reorder": 1}, {"scan_variant": 4, "force_weighted": 1},
-                 {"scan_variant": 3, "force_heavy_deg": 8, "reorder": 1}, {"scan_variant": 0, "force_weighted": 1, "reorder": 1}):
+    for opts in ({"scan_variant": 3, "cache_policy": 0}, {"scan_variant": 3}, {"scan_variant": 3, "reorder": 1},
+                 {"scan_variant": 3, "force_weighted": 1}, {"scan_variant": 4}, {"scan_variant": 4, "reorder": 1},
+                 {"scan_variant": 4, "force_weighted": 1}, {"scan_variant": 3, "force_heavy_deg": 8, "reorder": 1},
+                 {"scan_variant": 4, "force_weighted": 1, "reorder": 1}):
         res = run_single(gpu, parts, rowptr, edges, nv, **opts)
         assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
     for name in ("hand_weighted20_p1", "rgg_n16384_p1_w", "hand_loops_multi_p1", "hand_star41_p1", "hand_k66_p1"):
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
-        for var in (0, 3, 4):
+        for var in (3, 4):
             res = run_single(gpu, parts, rowptr, edges, nv, scan_variant=var)
             assert abs(res["modularity"] - float(case["modularity"])) <= 1e-6 and res["iters"] == case["iters"], (name, var)
+    g = gpu.LouvainGPU(0, 0, 1)
+    with pytest.raises(gpu.MvgpuError):
+        g.set_option("scan_variant", 0)              # the first-generation kernel is gone
+    g.close()
 
 
 def test_full_size_config2_matches_reference_trace(gpu):
@@ -215,7 +219,7 @@ def test_locality_renumbering_keeps_results(gpu, golden):
     for name in names:
         case = golden[name]
         nv, parts, rowptr, edges = as_single(case)
-        for opts in ({"reorder": 1, "region_size": 64}, {"reorder": 1, "region_size": 4096, "scan_variant": 0},
+        for opts in ({"reorder": 1, "region_size": 64}, {"reorder": 1, "region_size": 4096, "scan_variant": 3},
                      {"reorder": 1, "region_size": 32, "force_heavy_deg": 3}):
             res = run_single(gpu, parts, rowptr, edges, nv, **opts)
             assert res["timings"]["reordered"] == 1, (name, opts)

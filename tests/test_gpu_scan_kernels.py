@@ -90,3 +90,17 @@ def test_dense_and_skewed_graphs_against_oracle(gpu, variant):
             assert [int(x) for x in res["trace"]["chash"]] == [int(x) for x in ref["trace"]["chash"]]
         if res["info"]["maxdeg"] > 2048:                  # above every tile capacity: the high-degree kernel ran, unforced
             assert res["info"]["nheavy"] > 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_power_law_graphs_reach_the_high_degree_kernel_unforced(gpu, golden_rmat, variant):
+    """R-MAT graphs read the way `miniVite -f` reads them: hubs of degree 3 684 / 15 706 are far above every tile
+    capacity, so k_scan_heavy runs without the force_heavy_deg test hook; traces equal the unmodified reference's."""
+    for name in ("rmat_s14_p1", "rmat_s17_p1"):
+        case = golden_rmat[name]
+        nv, parts, rowptr, edges = as_single(case)
+        for opts in ({}, {"reorder": 1, "region_size": 128}):
+            res = run_single(gpu, parts, rowptr, edges, nv, scan_variant=variant, **opts)
+            assert res["info"]["maxdeg"] == case["maxdeg"] and res["info"]["nheavy"] > 0
+            assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+            assert repr(res["constant"]) == case["constant"]

@@ -121,3 +121,16 @@ def test_rgg_radius_matches_survey_table():
     assert abs(hg.rgg_radius(16384) - 1.249e-2) < 5e-6          # SURVEY.md section 8 config table (graph.hpp:629-631)
     assert abs(hg.rgg_radius(16777216) - 4.567e-4) < 5e-8
     assert abs(hg.rgg_radius(67108864, 8) - 2.341e-4) < 5e-8
+
+
+def test_oracle_matches_power_law_goldens(golden_rmat):
+    """R-MAT graphs (hubs of degree 3 684 and 15 706), plain and edge-balanced (-b) splits: the C restatement
+    reproduces the unmodified reference's traces bit for bit."""
+    from helpers import assert_trace_matches, case_graph
+    from oracle import oracle as O
+    for name, case in golden_rmat.items():
+        parts, rps, eds, _ = case_graph(case)
+        r = O.louvain(parts, rps, eds)
+        tr = [{"modularity": t["modularity"], "moved": t["moved"], "chash": t["chash"]} for t in r["trace"]]
+        assert_trace_matches(case, r["iters"], r["modularity"], tr, r["chash_final"])
+        assert repr(r["constant"]) == case["constant"], name
