@@ -225,6 +225,9 @@ def main():
     ap.add_argument("--compact-upload", type=int, default=-1, metavar="THREADS",
                     help="e2e leg: host threads that narrow unit-weight shards to 4-byte tails while the copy engine ships "
                          "them (library option compact_upload); 0 = ship the 16-byte records; default = min(32, cores/ranks)")
+    ap.add_argument("--upload-mode", type=int, default=2, choices=[1, 2],
+                    help="e2e leg, library option compact_upload: 1 = every chunk narrowed by host threads; 2 (default) = "
+                         "the copy engine additionally takes raw chunks from the far end whenever no narrowed chunk is ready")
     ap.add_argument("--ref-budget-s", type=float, default=420.0, help="wall-clock budget of the reference arm's runs")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
@@ -397,7 +400,7 @@ def main():
     # ---- e2e: host arrays -> H2D -> Louvain -> assignment D2H, through the public API
     cu_threads = args.compact_upload if args.compact_upload >= 0 else max(1, min(32, cores // max(world, 1)))
     if cu_threads > 0:
-        ctx.set_option("compact_upload", 1)
+        ctx.set_option("compact_upload", args.upload_mode)
         ctx.set_option("host_threads", cu_threads)
     e2e_t = []
     h_comm = torch.empty(sh.lnv, dtype=torch.int64).pin_memory().numpy()      # the user's (pinned) result buffer
@@ -473,7 +476,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": t_e2e * 1e3,
                     "h2d_bytes_per_step": h2d_total,
                     "path": "pinned host arrays -> mvgpu_upload_shard -> mvgpu_louvain -> mvgpu_get_communities (pinned int64 result)",
-                    "compact_upload_threads": cu_threads,
+                    "compact_upload_threads": cu_threads, "compact_upload_mode": args.upload_mode if cu_threads else 0,
                     "d2h_bytes_per_step": int(nv_total * 8 + 16)},
             "gpu_launches": launches_total, "clocks": clocks,
             "nvlink": None if N == 1 else {

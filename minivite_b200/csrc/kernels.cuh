@@ -687,6 +687,30 @@ __global__ void __launch_bounds__(256) k_fill_ones(double *w, long long n) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) w[e] = 1.0;
 }
 
+// device half of the compact upload: a raw chunk of 16-byte records -> int32 global tails + the statistics the host
+// pass (narrow.cpp) gathers for its chunks
+__global__ void __launch_bounds__(256) k_narrow_records(const Edge16 *rec, long long n, long long nv_global, long long base,
+                                                        long long bound, int32_t *dst, EdgeStats *st) {
+  unsigned long long nrem = 0;
+  unsigned int nonunit = 0, bad = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const double2 raw = __ldcs(reinterpret_cast<const double2 *>(rec + e));
+    const long long t = __double_as_longlong(raw.x);
+    dst[e] = (int32_t)t;
+    if (raw.y != 1.0) nonunit = 1;
+    if (t < 0 || t >= nv_global) bad = 1;
+    else if (t < base || t >= bound) nrem++;
+  }
+  nrem = warp_sum(nrem);
+  nonunit = __any_sync(0xffffffffu, nonunit);
+  bad = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (nrem) atomicAdd(&st->nremote, nrem);
+    if (nonunit) atomicOr(&st->nonunit, 1u);
+    if (bad) atomicOr(&st->bad_tail, 1u);
+  }
+}
+
 // same conversion for the compact upload format (int32 global tails, unit weights; see mvgpu_upload_shard)
 __global__ void __launch_bounds__(256) k_convert_tails32(const int32_t *gtails, long long lne, long long base, long long bound,
                                                          int32_t *tails, long long *remote_list, unsigned long long *remote_cursor) {
@@ -858,51 +882,36 @@ __global__ void __launch_bounds__(256) k_collect_heavy(int lnv, const uint32_t *
 #ifndef MV_BFS_SUB
 #define MV_BFS_SUB 4
 #endif
-#ifndef MV_BFS_LVL8
-#define MV_BFS_LVL8 1      // byte-per-vertex level array in front of the keys (see k_msbfs)
-#endif
 constexpr unsigned int kBfsRegionBits = 22;
 constexpr unsigned int kBfsUnreached = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, const int32_t *tails, uint32_t *key,
-                                               int region_stride, int max_levels, unsigned int *level_flags, uint8_t *lvl8) {
+                                               int region_stride, int max_levels, unsigned int *level_flags) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-  for (int v = gtid; v < lnv; v += gsz) {
-    const bool seed = v % region_stride == 0;
-    key[v] = seed ? (unsigned int)(v / region_stride) : kBfsUnreached;
-    lvl8[v] = seed ? 0 : 255;
-  }
+  for (int v = gtid; v < lnv; v += gsz)
+    key[v] = (v % region_stride == 0) ? (unsigned int)(v / region_stride) : kBfsUnreached;
   grid.sync();
   const int lane = threadIdx.x & 31;
-  // lvl8[v] = BFS level of v (255: not reached yet), one BYTE per vertex next to the 4-byte keys (MV_BFS_LVL8, default on).
-  // The keys alone cost one random 32-byte DRAM sector per edge probe -- 6.4 GB per run at config 2, nearly all of it for
-  // targets that were settled levels ago (profiles/r2_msbfs_sub4_summary.md) -- and one 67 MB sweep per level.  The byte
-  // array is a quarter of that, stays in L2, and answers both questions: the level sweep reads it instead of the
-  // keys, and a probe goes on to the key only if the target is not known to sit at a level <= the current one.  A
-  // stale 255 only costs the probe the filter would have saved; the keys (atomicMin on level<<22|region) still decide,
-  // so the result is the same deterministic minimum as before.
-  // Frontier vertices found by a warp are parked in shared memory and expanded MV_BFS_SUB at a time, 32 / MV_BFS_SUB lanes
-  // each, so that several adjacency reads and their dependent probes are in flight per warp.
+  // Every warp inspects 32 consecutive keys per step.  The frontier vertices it finds are parked in shared memory and
+  // expanded MV_BFS_SUB at a time, 32 / MV_BFS_SUB lanes each, so that several adjacency reads and their dependent
+  // key[] probes are in flight per warp (one vertex at a time, 32 lanes each, left two dependent memory round trips per
+  // frontier vertex exposed: 6.74 -> 6.05 ms for the renumbering at config 2 with 8 lanes per vertex).
+  // The kernel is bound by the random 32-byte key[] sectors of the edge probes (6.4 GB of DRAM reads per run at config 2,
+  // profiles/r2_msbfs_sub4_summary.md).  Two filters in front of the keys were measured and removed because the extra
+  // dependent load cost more than the sectors it saved: a bit per expanded vertex (6.05 -> 6.70 / 7.24 ms) and a byte
+  // per vertex holding its level (6.05 -> 6.61 ms), profiles/README.md.
   constexpr int kBfsSub = MV_BFS_SUB, kBfsLanes = 32 / kBfsSub;
   __shared__ uint32_t s_front[256 / 32][32][3];
   uint32_t(*front)[3] = s_front[threadIdx.x >> 5];
   for (int level = 0; level < max_levels; level++) {
     bool any = false;
-    const bool bytes = MV_BFS_LVL8 && level < 254;              // deeper searches fall back to the keys
-    const unsigned char next8 = (unsigned char)(level + 1);
     for (int vb = (gtid - lane); vb < lnv; vb += gsz) {
       const int v = vb + lane;
-      bool active = false;
       unsigned int k = kBfsUnreached;
-      if (bytes) {
-        active = v < lnv && __ldcg(lvl8 + v) == (unsigned char)level;
-        if (active) k = __ldcg(key + v);
-      } else {
-        if (v < lnv) k = __ldcg(key + v);
-        active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
-      }
+      if (v < lnv) k = __ldcg(key + v);
+      const bool active = (k != kBfsUnreached) && ((k >> kBfsRegionBits) == (unsigned int)level);
       const unsigned int m = __ballot_sync(0xffffffffu, active);
       if (m == 0) continue;
       any = true;
@@ -919,11 +928,7 @@ __global__ void __launch_bounds__(256) k_msbfs(int lnv, const uint32_t *rowptr, 
         const uint32_t e1 = front[i][2];
         for (uint32_t e = front[i][1] + (lane % kBfsLanes); e < e1; e += kBfsLanes) {
           const int w = tails[e];
-          if (w >= lnv) continue;
-          if (bytes) {
-            if (__ldcg(lvl8 + w) <= (unsigned char)level) continue;       // settled at this level or before: its key is smaller
-            if (__ldcg(key + w) > nk) { atomicMin(&key[w], nk); lvl8[w] = next8; }
-          } else if (__ldcg(key + w) > nk) atomicMin(&key[w], nk);
+          if (w < lnv && __ldcg(key + w) > nk) atomicMin(&key[w], nk);
         }
       }
       __syncwarp();

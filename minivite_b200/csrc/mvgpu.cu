@@ -111,6 +111,8 @@ struct mvgpu_ctx {
   DevBuf<Edge16> gen_edges;
   // compact upload format (unit-weight shards): int32 global tails, staged through pinned chunks
   DevBuf<int32_t> in_tails32;
+  DevBuf<Edge16> raw_ring;             // compact upload: raw chunks narrowed on the device (two slots)
+  long long raw_chunks = 0;
   DevBuf<long long> wide;
   void *h_bounce[2] = {nullptr, nullptr};
   const int32_t *d_tails32 = nullptr;
@@ -128,7 +130,7 @@ struct mvgpu_ctx {
   DevBuf<double> weights;
   DevBuf<int32_t> self_i;
   // locality renumbering
-  DevBuf<uint32_t> bfs_key, bfs_visited, sortkey, sortkey2, deg_new, rowptr2;
+  DevBuf<uint32_t> bfs_key, sortkey, sortkey2, deg_new, rowptr2;
   DevBuf<int32_t> ids, perm, inv, lab, tails2, final_orig;
   DevBuf<double> weights2;
   DevBuf<unsigned int> level_flags;
@@ -175,6 +177,7 @@ struct mvgpu_ctx {
   unsigned last_gens[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // options
   int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 4, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
+  long long opt_upload_chunk = 4LL << 20;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
@@ -636,10 +639,8 @@ int setup_run(mvgpu_ctx *c) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_msbfs, 256, 0));
         if (occ < 1) return fail("k_msbfs cannot be made resident");
         int ilnv = (int)lnv, stride = c->opt_region, ml = max_levels;
-        TRY(c->bfs_visited.ensure((size_t)(lnv + 3) / 4 + 1));      // one byte per vertex
         const uint32_t *rp = src_rowptr; const int32_t *tl = src_tails; uint32_t *key = c->bfs_key.p; unsigned int *lf = c->level_flags.p;
-        uint8_t *lvl8 = reinterpret_cast<uint8_t *>(c->bfs_visited.p);
-        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf, &lvl8};
+        void *args[] = {&ilnv, &rp, &tl, &key, &stride, &ml, &lf};
         CK(cudaLaunchCooperativeKernel((void *)k_msbfs, dim3(occ * nsm), dim3(256), args, 0, s));
         // sort by (region, level): only the bits that can be set take part (one radix pass less than a 32-bit sort)
         const long long nregions = (lnv + stride - 1) / stride;
@@ -1006,14 +1007,14 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->hc.close_comm();
   for (cudaEvent_t e : c->events) cudaEventDestroy(e);
   if (c->h_stage) cudaFreeHost(c->h_stage);
-  c->in_tails32.release(); c->wide.release();
+  c->in_tails32.release(); c->wide.release(); c->raw_ring.release();
   for (int b = 0; b < 2; b++) if (c->h_bounce[b]) cudaFreeHost(c->h_bounce[b]);
   c->gen_rowptr.release(); c->gen_edges.release();
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
   c->scratch.release(); c->cub_tmp.release(); c->coll_tmp.release(); c->sorted_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
-  c->bfs_key.release(); c->bfs_visited.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
+  c->bfs_key.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
   c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
   c->weights2.release(); c->level_flags.release();
   c->p2p.release();
@@ -1063,9 +1064,9 @@ int mvgpu_comm_init(mvgpu_ctx *c, const void *id128) {
 // cudaMemcpyAsync, so the copy engine and the cores overlap.  Validation (weights all 1.0, tails in range) and the
 // count of non-owned tails happen in the same pass.  Returns 1 when the shard does not qualify (then the full
 // records are uploaded), 0 on success, <0 on CUDA errors.
-static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const void *edge_list) {
+static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const void *edge_list, long long *bytes_copied) {
   const Edge16 *E = reinterpret_cast<const Edge16 *>(edge_list);
-  const long long CH = 4LL << 20;                                // edges per chunk (64 MB read, 16 MB staged)
+  const long long CH = c->opt_upload_chunk;                      // edges per chunk (default 4 Mi: 64 MB read, 16 MB staged)
   const long long nchunks = (lne + CH - 1) / CH;
   if ((size_t)lne > c->h_stage_cap) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1074,17 +1075,45 @@ static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const vo
     c->h_stage_cap = (size_t)lne;
   }
   if (c->in_tails32.ensure(lne + 4)) return -1;
+  if (c->raw_ring.ensure((size_t)2 * CH)) return -1;             // two raw chunks in flight on the device
+  if (c->scratch.ensure(sizeof(Scalars))) return -1;
+  Scalars *d_sc = reinterpret_cast<Scalars *>(c->scratch.p);
+  if (cudaMemsetAsync(&d_sc->st, 0, sizeof(EdgeStats), c->stream) != cudaSuccess) return -1;
   int32_t *stage = reinterpret_cast<int32_t *>(c->h_stage);
   const long long base = c->base, bound = c->bound;
   const int nthreads = (int)std::max<long long>(1, std::min<long long>(c->opt_host_threads > 0 ? c->opt_host_threads : 8, nchunks));
+  // The chunks are consumed from both ends.  Host threads narrow chunks from the FRONT (16-byte records -> 4-byte
+  // tails in the pinned staging array, shipped as soon as they are ready); whenever no narrowed chunk is ready the
+  // calling thread hands the copy engine a RAW chunk from the BACK instead (64 MB of records into a two-slot device
+  // ring, narrowed there by k_narrow_records).  The copy engine never idles while the cores narrow, the cores never
+  // idle while the link is busy, and the meeting point adapts to whatever cores and link the box has.  Front and back
+  // share one atomic word so that no chunk is claimed twice.
   std::vector<std::atomic<int>> done(nchunks);
   for (auto &d : done) d.store(0);
-  std::atomic<long long> next{0}, nremote{0};
+  std::atomic<unsigned long long> claim{0};                      // front << 32 | back
+  std::atomic<long long> nremote{0};
   std::atomic<int> bad{0};
+  auto claim_front = [&]() -> long long {
+    unsigned long long v = claim.load();
+    for (;;) {
+      const unsigned long long f = v >> 32, bk = v & 0xffffffffULL;
+      if ((long long)(f + bk) >= nchunks) return -1;
+      if (claim.compare_exchange_weak(v, ((f + 1) << 32) | bk)) return (long long)f;
+    }
+  };
+  auto claim_back = [&]() -> long long {
+    unsigned long long v = claim.load();
+    for (;;) {
+      const unsigned long long f = v >> 32, bk = v & 0xffffffffULL;
+      if ((long long)(f + bk) >= nchunks) return -1;
+      if (claim.compare_exchange_weak(v, (f << 32) | (bk + 1))) return nchunks - 1 - (long long)bk;
+    }
+  };
   auto worker = [&]() {
     for (;;) {
-      const long long i = next.fetch_add(1);
-      if (i >= nchunks || bad.load(std::memory_order_relaxed)) break;
+      if (bad.load(std::memory_order_relaxed)) break;
+      const long long i = claim_front();
+      if (i < 0) break;
       const long long off = i * CH, n = std::min<long long>(CH, lne - off);
       long long nrem = 0;
       int b = 0;
@@ -1097,19 +1126,50 @@ static int upload_compact(mvgpu_ctx *c, int64_t nv_global, int64_t lne, const vo
   std::vector<std::thread> pool;
   for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
   int rc = 0;
-  for (long long i = 0; i < nchunks && !rc; i++) {
-    while (!done[i].load(std::memory_order_acquire)) {
-      if (bad.load(std::memory_order_relaxed)) break;
-      std::this_thread::yield();
+  long long next_front = 0, raw_issued = 0, copied = 0;
+  cudaEvent_t raw_ev[2] = {get_event(c, 2), get_event(c, 3)};     // completion of the raw chunk that used ring slot k
+  const bool use_raw = c->opt_compact_upload >= 2;
+  while (!rc && !bad.load(std::memory_order_relaxed)) {
+    const unsigned long long v = claim.load();
+    const long long f = (long long)(v >> 32), bk = (long long)(v & 0xffffffffULL);
+    if (next_front < f && done[next_front].load(std::memory_order_acquire)) {          // a narrowed chunk is ready: ship it
+      const long long off = next_front * CH, n = std::min<long long>(CH, lne - off);
+      if (cudaMemcpyAsync(c->in_tails32.p + off, stage + off, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = -1;
+      copied += (long long)sizeof(int32_t) * n;
+      next_front++;
+      continue;
     }
-    if (bad.load()) break;
-    const long long off = i * CH, n = std::min<long long>(CH, lne - off);
-    if (cudaMemcpyAsync(c->in_tails32.p + off, stage + off, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = -1;
+    if (next_front >= f && f + bk >= nchunks) break;                                    // everything claimed and shipped
+    // nothing narrowed is ready: keep the link busy with a raw chunk, at most two in flight
+    if (use_raw && (raw_issued < 2 || cudaEventQuery(raw_ev[raw_issued & 1]) == cudaSuccess)) {
+      const long long i = claim_back();
+      if (i >= 0) {
+        const long long off = i * CH, n = std::min<long long>(CH, lne - off);
+        Edge16 *slot = c->raw_ring.p + (raw_issued & 1) * CH;
+        if (cudaMemcpyAsync(slot, E + off, sizeof(Edge16) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = -1;
+        k_narrow_records<<<grid_for(n, 256, c->num_sms, 16), 256, 0, c->stream>>>(slot, n, nv_global, base, bound, c->in_tails32.p + off, &d_sc->st);
+        if (cudaEventRecord(raw_ev[raw_issued & 1], c->stream) != cudaSuccess) rc = -1;
+        copied += (long long)sizeof(Edge16) * n;
+        raw_issued++;
+        continue;
+      }
+    }
+    std::this_thread::yield();
   }
   for (auto &th : pool) th.join();
   if (rc) return rc;
   if (bad.load()) { cudaStreamSynchronize(c->stream); return 1; }
-  c->in_nremote = nremote.load();
+  long long nrem_dev = 0;
+  if (raw_issued) {
+    EdgeStats hs;
+    if (cudaMemcpyAsync(&hs, &d_sc->st, sizeof hs, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    if (hs.nonunit || hs.bad_tail) return 1;
+    nrem_dev = (long long)hs.nremote;
+  }
+  c->in_nremote = nremote.load() + nrem_dev;
+  c->raw_chunks = raw_issued;
+  *bytes_copied = copied;
   return 0;
 }
 
@@ -1125,8 +1185,9 @@ int mvgpu_upload_shard(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, in
   c->d_tails32 = nullptr;
   c->d_edges = nullptr;
   int compact = 1;
+  long long compact_bytes = 0;
   if (c->opt_compact_upload && !c->opt_force_weighted && lne > 0) {
-    compact = upload_compact(c, nv_global, lne, edge_list);
+    compact = upload_compact(c, nv_global, lne, edge_list, &compact_bytes);
     if (compact < 0) return fail(std::string("compact upload: ") + cudaGetErrorString(cudaGetLastError()));
   }
   if (compact == 0) c->d_tails32 = c->in_tails32.p;
@@ -1140,7 +1201,7 @@ int mvgpu_upload_shard(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, in
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, a, b));
   c->h2d_s = ms * 1e-3;
-  c->h2d_bytes = (long long)sizeof(long long) * (lnv + 1) + (compact == 0 ? (long long)sizeof(int32_t) : (long long)sizeof(Edge16)) * lne;
+  c->h2d_bytes = (long long)sizeof(long long) * (lnv + 1) + (compact == 0 ? compact_bytes : (long long)sizeof(Edge16) * lne);
   c->d_rowptr64 = c->in_rowptr.p;
   return 0;
 }
@@ -1325,6 +1386,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "compact_upload") c->opt_compact_upload = (int)value;
   else if (n == "host_threads") c->opt_host_threads = (int)value;
   else if (n == "first_iter") c->opt_first_iter = value != 0;
+  else if (n == "upload_chunk") { if (value < 256 || (value & 3)) return fail("upload_chunk must be a multiple of 4, >= 256"); c->opt_upload_chunk = value; }
   else if (n == "host_transport") { if (c->comm || c->hc.is_open()) return fail("host_transport must be set before mvgpu_comm_init"); c->opt_host_transport = value != 0; }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);

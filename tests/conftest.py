@@ -17,6 +17,15 @@ os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
+# libmvgpu.so binds NCCL at run time by soname (csrc/nccl_dyn.h).  torch brings its own, newer libnccl.so.2: whichever is
+# loaded first wins for the whole process, and torch cannot start on the system copy.  Tests that import torch late
+# (torch.multiprocessing for the multi-process cases) therefore need torch's copy to be the first one in.
+try:
+    import torch  # noqa: F401,E402
+except Exception:  # pragma: no cover  (CPU-only environments without torch still run the oracle / ABI tests)
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

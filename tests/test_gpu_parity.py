@@ -245,10 +245,18 @@ def test_upload_formats_agree(gpu, golden):
             res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=cu, host_threads=4)
             assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
             assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + (4 if cu else 16) * len(edges)
+        # compact_upload=2: host threads narrow chunks from the front while the copy engine takes raw chunks from the back
+        # (narrowed on the device); small chunks so that both ends are busy on a test-sized graph
+        for threads, chunk in ((1, 256), (3, 1024), (8, 4096)):
+            res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=2, host_threads=threads, upload_chunk=chunk)
+            assert_trace_matches(case, res["iters"], res["modularity"], res["trace"], None, None)
+            lo, hi = 8 * (nv + 1) + 4 * len(edges), 8 * (nv + 1) + 16 * len(edges)
+            assert lo <= res["timings"]["h2d_bytes"] <= hi
     case = golden["rgg_n16384_p1_w"]
     nv, parts, rowptr, edges = as_single(case)
-    res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=1)
-    assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + 16 * len(edges) and res["timings"]["unit_weight"] == 0
+    for cu, extra in ((1, {}), (2, {"upload_chunk": 1024, "host_threads": 2})):
+        res = run_single(gpu, parts, rowptr, edges, nv, compact_upload=cu, **extra)
+        assert res["timings"]["h2d_bytes"] == 8 * (nv + 1) + 16 * len(edges) and res["timings"]["unit_weight"] == 0
 
 
 def test_full_size_config3_random_edges(gpu):
