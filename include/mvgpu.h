@@ -82,10 +82,13 @@ int mvgpu_upload_shard(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, 
 int mvgpu_attach_shard_device(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
                               const int64_t *d_edge_indices, const void *d_edge_list);
 
-/* Device-side GenerateRGG (graph.hpp:584-1213, default RNG, no -l / -p): builds this rank's strip of the graph
+/* Device-side GenerateRGG (graph.hpp:584-1213, no -p): builds this rank's strip of the graph
  * `miniVite -n nv_global` creates on nranks ranks directly in HBM, bit-identical to the reference generator, and
  * attaches it as the context's shard.  unit_weight = 0 gives Euclidean edge weights (-w).  *lne_out: local edges. */
 int mvgpu_generate_rgg_shard(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int64_t *lne_out);
+/* Same with the choice of random numbers: lcg = 1 draws the coordinates from the reference's LCG class like
+ * `miniVite -n nv_global -l` (utils.hpp:118-303, graph.hpp:703-729), lcg = 0 is the default engine. */
+int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int lcg, int64_t *lne_out);
 /* Copy the shard's reference-format arrays (lnv+1 offsets, lne 16-byte records) back to the host. */
 int mvgpu_download_shard(mvgpu_ctx *ctx, int64_t *edge_indices, void *edge_list);
 
@@ -102,9 +105,11 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
 /* Options: "trace" (0/1: record moved/chash per iteration, default 0), "max_iters" (safety cap,
  * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
- * "scan_variant" (4 = k_scan_pw: persistent warps fed by TMA bulk copies (default); 3 = k_scan_ws: one CTA per
- * 128-vertex tile, the default of round 1; identical results), "first_iter" (1 (default): iteration 1 of a simple
- * unit-weight graph uses the singleton-community reduction of k_scan_pw; 0: the general reduction; identical results),
+ * "scan_variant" (5 = k_scan_pq (default): persistent warps fed by TMA bulk copies, boundary vertices reduced from a
+ * per-warp ring -- unit weights; iteration 1 and weighted graphs run k_scan_pw; 4 = k_scan_pw throughout; 3 =
+ * k_scan_ws: one CTA per 128-vertex tile, the default of round 1; identical results), "first_iter" (1 (default):
+ * iteration 1 of a simple unit-weight graph uses the singleton-community reduction of k_scan_pw; 0: the general
+ * reduction; identical results), "upload_chunk" (edges per chunk of the compact upload, default 4 Mi; test hook),
  * "cache_policy" (bit2 = L2 evict_first hint on the streamed arrays of k_scan_ws; other bits are accepted and
  * ignored; default 5), "reorder" (0 never, 1 always, 2 auto (default): renumber vertices for memory
  * locality when the given numbering has none -- layout only, results are identical), "region_size" (target
@@ -112,8 +117,9 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
  * flags in peer memory over NVLink (default), 0 = NCCL all-to-all-v + all-reduce), "host_transport" (set before
  * mvgpu_comm_init; 1: the setup-time exchanges go through a shared-memory segment of the host instead of NCCL --
  * required when several ranks share one device, which NCCL refuses; needs comm_mode 1; default 0), "compact_upload" (1:
- * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 0 (default) = the 16-byte
- * records as they are), "host_threads" (threads of that host pass, default 8).
+ * mvgpu_upload_shard sends unit-weight shards as 4-byte tails narrowed on the host; 2: the copy engine additionally
+ * takes raw chunks from the far end of the array whenever no narrowed chunk is ready (narrowed on the device);
+ * 0 (default) = the 16-byte records as they are), "host_threads" (threads of that host pass, default 8).
  * The environment variable MVGPU_OPTIONS="name=value,name=value" presets options for every context of the process. */
 /* In a multi-rank run every rank must set the same options (they change which collectives a run issues). */
 int mvgpu_set_option(mvgpu_ctx *ctx, const char *name, int64_t value);

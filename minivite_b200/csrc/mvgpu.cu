@@ -29,6 +29,7 @@
 #include "host_comm.hpp"
 #include "kernels.cuh"
 #include "scan_pipe.cuh"
+#include "scan_queue.cuh"
 #include "nccl_dyn.h"
 #include "rgg_gpu.cuh"
 
@@ -176,7 +177,7 @@ struct mvgpu_ctx {
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned last_gens[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 4, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 5, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
   long long opt_upload_chunk = 4LL << 20;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
@@ -401,7 +402,20 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp, bool first) {
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
-  if (tiles > 0 && c->opt_scan_variant == 4) {
+  if (tiles > 0 && c->opt_scan_variant == 5 && UNIT && !first) {
+    // k_scan_pw's pipeline with a per-warp ring of hard vertices (scan_queue.cuh); iteration 1 and the weighted path
+    // stay with k_scan_pw
+    static int pq_ctas_per_sm = 0;
+    if (!pq_ctas_per_sm) {
+      CK(cudaFuncSetAttribute(k_scan_pq<MULTI, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pq_smem_bytes()));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pq_ctas_per_sm, k_scan_pq<MULTI, TRACE>, kPwWarps * 32, pq_smem_bytes()));
+      if (pq_ctas_per_sm < 1) return fail("k_scan_pq cannot be made resident");
+    }
+    const int ngroups = (int)((c->lnv + 31) / 32);
+    const int grid = std::min((ngroups + kPwWarps - 1) / kPwWarps, pq_ctas_per_sm * c->num_sms);
+    k_scan_pq<MULTI, TRACE><<<grid, kPwWarps * 32, pq_smem_bytes(), c->stream>>>(sp, ngroups);
+    c->tm.kernel_launches++; c->tm.scan_launches++;
+  } else if (tiles > 0 && c->opt_scan_variant >= 4) {
     // persistent warps, TMA-fed double buffer (scan_pipe.cuh): one CTA slot per resident block, warps stride over groups
     static int pw_ctas_per_sm = 0;
     if (!pw_ctas_per_sm) {
@@ -688,9 +702,11 @@ int setup_run(mvgpu_ctx *c) {
   c->a_rowptr = src_rowptr; c->a_tails = src_tails; c->a_weights = src_weights;
 
   // state arrays
+  // sized for the bound the collective "does an exported array have to grow?" test can evaluate before the ghosts are
+  // known (lnv + #non-owned edge tails >= lnv + nghost), so that a repeated run never looks like a growing one
   const long long nslots = lnv + c->nghost;
-  TRY(c->comm_a.ensure(nslots));
-  TRY(c->comm_b.ensure(nslots));
+  TRY(c->comm_a.ensure(std::max(nslots, lnv + nremote)));
+  TRY(c->comm_b.ensure(std::max(nslots, lnv + nremote)));
   if (c->unit) { TRY(c->cdeg.ensure(lnv)); TRY(c->csize.ensure(lnv)); TRY(c->upd.ensure(lnv)); TRY(c->self_i.ensure(lnv)); }
   else { TRY(c->cinfo_w.ensure(lnv)); TRY(c->usize.ensure(lnv)); TRY(c->udeg.ensure(lnv)); TRY(c->vdeg.ensure(lnv)); TRY(c->self_d.ensure(lnv)); }
   TRY(c->acc.ensure((size_t)c->opt_max_iters + 2));
@@ -712,7 +728,7 @@ int setup_run(mvgpu_ctx *c) {
 
   // high-degree vertices
   // largest degree the tile kernels take: one staging buffer (minus the 16-byte alignment slack of the bulk copies)
-  const long long tile_cap = c->opt_scan_variant == 4 ? (c->unit ? PwCap<true>::value : PwCap<false>::value) - 4 : kECap;
+  const long long tile_cap = c->opt_scan_variant >= 4 ? (c->unit ? PwCap<true>::value : PwCap<false>::value) - 4 : kECap;
   const long long heavy_deg = (c->opt_force_heavy_deg > 0) ? std::min<long long>(c->opt_force_heavy_deg, tile_cap) : tile_cap;
   c->nheavy = 0;
   if (c->maxdeg > heavy_deg) {
@@ -818,7 +834,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     cudaEvent_t e0 = get_event(c, ev++), e1 = get_event(c, ev++), e2 = get_event(c, ev++), e3 = get_event(c, ev++);
     CK(cudaEventRecord(e0, s));
     // iteration 1 of a simple graph: every community is a singleton (scan_pipe.cuh, FIRST)
-    TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant == 4));
+    TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant >= 4));
     CK(cudaEventRecord(e1, s));
     const bool p2p = c->nranks > 1 && c->opt_comm_mode == 1;
     if (c->nranks > 1) {
@@ -1222,6 +1238,10 @@ int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *pa
 
 // ---- section 8(f) rank 1: the reference's GenerateRGG on the device (rgg_gpu.cuh) ---------------------------------
 int mvgpu_generate_rgg_shard(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int64_t *lne_out) {
+  return mvgpu_generate_rgg_shard_ex(c, nv_global, unit_weight, 0, lne_out);
+}
+
+int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int lcg, int64_t *lne_out) {
   if (!c) return fail("null ctx");
   CK(cudaSetDevice(c->device));
   const int p = c->nranks, r = c->rank;
@@ -1241,6 +1261,25 @@ int mvgpu_generate_rgg_shard(mvgpu_ctx *c, int64_t nv_global, int unit_weight, i
   P.rn = (rc + rt) / 2.0;
   P.rec_np = (double)(1.0 / (double)p);
   if (!(P.rec_np > P.rn)) return fail("RGG radius does not fit the strip height (1/p > rn violated)");
+  if (lcg) {                                           // utils.hpp:146-218 as host/rgg.hpp restates it
+    P.lcg = 1;
+    const int64_t M = 2147483647LL, A = 16807LL;
+    const int64_t x0 = (int64_t)P.seed;
+    const uint64_t len = 2ULL * (uint64_t)P.n;
+    for (int k = 0; k < 3; k++) {
+      const int sr = r - 1 + k;
+      if (sr < 0 || sr >= p) { P.lcg_first[k] = 1; continue; }
+      int64_t first;
+      if (sr == 0) first = x0;
+      else {
+        uint64_t acc = 1, base = (uint64_t)A, e = len * (uint64_t)sr;
+        while (e) { if (e & 1) acc *= base; base *= base; e >>= 1; }
+        first = (int64_t)((uint64_t)x0 * acc) % M;
+      }
+      P.lcg_first[k] = (unsigned long long)(first < 0 ? -first : first);
+    }
+    P.lcg_mult = 1.0 / (double)(1.0 + (double)(M - 1));
+  }
   {                                                    // divisor of std::generate_canonical<double,53>(minstd_rand0)
     const long double rr = 2147483646.0L;
     double tmp = 1.0;
@@ -1262,10 +1301,10 @@ int mvgpu_generate_rgg_shard(mvgpu_ctx *c, int64_t nv_global, int unit_weight, i
   if (ncells + 1 >= (1LL << 31) || P.n >= (1LL << 31)) return fail("RGG too large for the device generator");
   cudaStream_t s = c->stream;
   const int nsm = c->num_sms;
-  DevBuf<double> X, UY, cx, cy;
+  DevBuf<double> X, UY, cx, cy;                        // X, UY: coordinates of up to three strips (own + neighbours)
   DevBuf<long long> cgid, deg;
   DevBuf<unsigned int> cnt, cstart;
-  TRY(X.ensure(P.n)); TRY(UY.ensure(P.n)); TRY(cnt.ensure(ncells + 1)); TRY(cstart.ensure(ncells + 1)); TRY(deg.ensure(P.n + 1));
+  TRY(X.ensure(3 * P.n)); TRY(UY.ensure(3 * P.n)); TRY(cnt.ensure(ncells + 1)); TRY(cstart.ensure(ncells + 1)); TRY(deg.ensure(P.n + 1));
   k_rgg_points<<<grid_for(P.n, 256, nsm), 256, 0, s>>>(P, X.p, UY.p);
   CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned int) * (ncells + 1), s));
   k_rgg_bin<<<grid_for(P.n, 256, nsm), 256, 0, s>>>(P, X.p, UY.p, 0, cnt.p, nullptr, nullptr, nullptr, nullptr);
@@ -1379,7 +1418,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
   else if (n == "force_weighted") c->opt_force_weighted = value != 0;
   else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
-  else if (n == "scan_variant") { if (value != 3 && value != 4) return fail("scan_variant must be 4 (k_scan_pw, default) or 3 (k_scan_ws)"); c->opt_scan_variant = (int)value; }
+  else if (n == "scan_variant") { if (value < 3 || value > 5) return fail("scan_variant must be 5 (k_scan_pq, default), 4 (k_scan_pw) or 3 (k_scan_ws)"); c->opt_scan_variant = (int)value; }
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else if (n == "reorder") c->opt_reorder = (int)value;
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;

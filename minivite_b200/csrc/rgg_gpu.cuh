@@ -3,7 +3,10 @@
 // Builds strip `rank` of the graph `miniVite -n nv` creates on `nranks` ranks (reference GenerateRGG,
 // graph.hpp:584-1213, default RNG path, no -l / -p) directly in HBM, in the reference's own array format
 // (int64 rowptr[lnv+1], {int64 tail; double weight}[lne]), bit-identical to the reference generator and to this
-// repo's host generator (host/rgg.hpp):
+// repo's host generator (host/rgg.hpp).  `-l` (the reference's LCG class, utils.hpp:118-303) is supported too: rank r's
+// coordinates are entries [2 n r, 2 n (r+1)) of x <- 16807 x mod 2^31-1, its first entry coming from the reference's
+// wrapping 64-bit matrix power (evaluated on the host, handed over as |first|); every strip has its own point pattern
+// there, so coordinates are kept per strip.  Default RNG path:
 //   * coordinates: minstd_rand0 (x <- 16807 x mod 2^31-1) seeded with reseeder(1); vertex i consumes outputs
 //     4i+1..4i+4 (two per double, std::generate_canonical<double,53>); every strip restarts from the same seed
 //     (graph.hpp:680-700).  The generator is a pure multiplicative LCG, so thread i jumps to its position with one
@@ -32,6 +35,9 @@ struct RggParams {
   long long ncell;           // cells per unit length
   long long row0, nrows;     // slab of cell rows this strip can reach
   double ylo, yhi;           // candidate band
+  int lcg;                   // -l: coordinates from the reference's LCG stream instead of minstd_rand0 + generate_canonical
+  unsigned long long lcg_first[3];   // |first entry| of the strips rank-1, rank, rank+1 (utils.hpp:146-218)
+  double lcg_mult;           // 1 / (1 + (M - 1)) as the reference evaluates it
 };
 
 __device__ __forceinline__ unsigned long long mulmod31(unsigned long long a, unsigned long long b) {
@@ -69,25 +75,45 @@ __device__ __forceinline__ long long cell_of(double v, long long ncell) {
   return c < 0 ? 0 : (c >= ncell ? ncell - 1 : c);
 }
 
-// X (shared by all strips) and canonical Y
-__global__ void __launch_bounds__(256) k_rgg_points(RggParams p, double *X, double *UY) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+// coordinates of local index i of strip s (s in [rank-1, rank+1]): x and absolute y
+__device__ __forceinline__ void strip_point(long long i, int s, const RggParams &p, double &x, double &y) {
+  if (!p.lcg) {
     double ux, uy;
     point_canon(i, p, ux, uy);
-    X[i] = __dadd_rn(__dmul_rn(ux, 1.0), 0.0);
-    UY[i] = uy;
+    x = __dadd_rn(__dmul_rn(ux, 1.0), 0.0);
+    y = strip_y(uy, s, p);
+    return;
   }
+  // utils.hpp:118-303 as the host generator restates it (host/rgg.hpp strip_points): entry k of the strip's stream is
+  // first * 16807^k mod M with C++'s sign-preserving %, only its magnitude is used
+  const unsigned long long f = p.lcg_first[s - p.rank + 1];
+  const unsigned long long ax = mulmod31(f, powmod31(16807ULL, (unsigned long long)i));
+  const unsigned long long ay = mulmod31(f, powmod31(16807ULL, (unsigned long long)(p.n + i)));
+  x = __dmul_rn((double)ax, p.lcg_mult);
+  const double lo = __dmul_rn((double)s, p.rec_np);
+  y = __dadd_rn(lo, __dmul_rn(p.rec_np, __dmul_rn((double)ay, p.lcg_mult)));
+}
+
+// coordinates of the own and the two adjacent strips: X3/Y3[(s - s0) * n + i]
+__global__ void __launch_bounds__(256) k_rgg_points(RggParams p, double *X3, double *Y3) {
+  const int s0 = max(0, p.rank - 1), s1 = min(p.nranks - 1, p.rank + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x)
+    for (int s = s0; s <= s1; s++) {
+      double x, y;
+      strip_point(i, s, p, x, y);
+      X3[(long long)(s - s0) * p.n + i] = x;
+      Y3[(long long)(s - s0) * p.n + i] = y;
+    }
 }
 
 // candidates = all points of the own strip + the points of the adjacent strips inside the band [ylo, yhi];
 // pass 0 counts per cell, pass 1 scatters (cell-sorted arrays cx, cy, cgid)
-__global__ void __launch_bounds__(256) k_rgg_bin(RggParams p, const double *X, const double *UY, int pass, unsigned int *cell_cnt,
+__global__ void __launch_bounds__(256) k_rgg_bin(RggParams p, const double *X3, const double *Y3, int pass, unsigned int *cell_cnt,
                                                  const unsigned int *cell_start, double *cx, double *cy, long long *cgid) {
   const int s0 = max(0, p.rank - 1), s1 = min(p.nranks - 1, p.rank + 1);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const double x = X[i], uy = UY[i];
     for (int s = s0; s <= s1; s++) {
-      const double y = strip_y(uy, s, p);
+      const double x = X3[(long long)(s - s0) * p.n + i], y = Y3[(long long)(s - s0) * p.n + i];
       if (y < p.ylo || y > p.yhi) continue;
       const long long row = cell_of(y, p.ncell);
       if (row < p.row0 || row >= p.row0 + p.nrows) continue;
@@ -103,11 +129,12 @@ __global__ void __launch_bounds__(256) k_rgg_bin(RggParams p, const double *X, c
 
 // neighbours of local vertex i: pass 0 counts (deg), pass 1 writes {tail, weight} records, then sorts them by tail
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_rgg_neighbours(RggParams p, const double *X, const double *UY, const unsigned int *cell_start,
+__global__ void __launch_bounds__(128) k_rgg_neighbours(RggParams p, const double *X3, const double *Y3, const unsigned int *cell_start,
                                                         const double *cx, const double *cy, const long long *cgid, int unit,
                                                         long long *deg_or_rowptr, Edge16 *edges) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const double xi = X[i], yi = strip_y(UY[i], p.rank, p);
+    const long long own = (long long)(p.rank - max(0, p.rank - 1)) * p.n;
+    const double xi = X3[own + i], yi = Y3[own + i];
     const long long row = cell_of(yi, p.ncell), col = cell_of(xi, p.ncell);
     const long long c0 = max(0LL, col - 1), c1 = min(p.ncell - 1, col + 1);
     long long cnt = 0;

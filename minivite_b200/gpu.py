@@ -27,7 +27,7 @@ class Timings(ctypes.Structure):
 
 
 EXPORTS = ["mvgpu_last_error", "mvgpu_device_count", "mvgpu_create", "mvgpu_destroy", "mvgpu_get_unique_id",
-           "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_generate_rgg_shard",
+           "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_generate_rgg_shard", "mvgpu_generate_rgg_shard_ex",
            "mvgpu_download_shard", "mvgpu_louvain",
            "mvgpu_get_communities", "mvgpu_get_communities_device", "mvgpu_set_option", "mvgpu_get_trace",
            "mvgpu_get_timings", "mvgpu_get_scan_times", "mvgpu_get_constant", "mvgpu_get_shard_info", "mvgpu_dist_louvain_method"]
@@ -52,6 +52,7 @@ def lib():
         L.mvgpu_upload_shard.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.mvgpu_attach_shard_device.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.mvgpu_generate_rgg_shard.argtypes = [vp, i64, ci, ctypes.POINTER(i64)]
+        L.mvgpu_generate_rgg_shard_ex.argtypes = [vp, i64, ci, ci, ctypes.POINTER(i64)]
         L.mvgpu_download_shard.argtypes = [vp, vp, vp]
         L.mvgpu_louvain.argtypes = [vp, dbl, dbl, ctypes.POINTER(ci), ctypes.POINTER(dbl)]
         L.mvgpu_get_communities.argtypes = [vp, vp]
@@ -124,10 +125,10 @@ class LouvainGPU:
         self.lnv = int(lnv)
         self._keep = keepalive
 
-    def generate_rgg(self, nv_global, unit_weight=True):
-        """Build this rank's strip of `miniVite -n nv_global` on the device (reference GenerateRGG); returns lne."""
+    def generate_rgg(self, nv_global, unit_weight=True, lcg=False):
+        """Build this rank's strip of `miniVite -n nv_global [-w] [-l]` on the device (reference GenerateRGG); returns lne."""
         lne = ctypes.c_int64(0)
-        _ck(lib().mvgpu_generate_rgg_shard(self._h, int(nv_global), int(bool(unit_weight)), ctypes.byref(lne)))
+        _ck(lib().mvgpu_generate_rgg_shard_ex(self._h, int(nv_global), int(bool(unit_weight)), int(bool(lcg)), ctypes.byref(lne)))
         self.lnv = int(nv_global) // self.nranks
         self._lne = lne.value
         return lne.value

@@ -86,7 +86,7 @@ def test_partition_invariance_on_one_device(golden):
 
 
 def test_options_on_one_device(golden):
-    for opts in ({"reorder": 1, "region_size": 64}, {"scan_variant": 3}, {"scan_variant": 3, "reorder": 1, "region_size": 64},
+    for opts in ({"reorder": 1, "region_size": 64}, {"scan_variant": 3}, {"scan_variant": 4}, {"scan_variant": 3, "reorder": 1, "region_size": 64},
                  {"first_iter": 0}, {"force_heavy_deg": 8}, {"force_weighted": 1}, {"compact_upload": 1}):
         check(run_threads(golden, "rgg_n16384_p2", 2, **opts), golden["rgg_n16384_p2"])
     res = run_threads(golden, "file_rgg_n16384_s2_w_p2", 2)

@@ -1,5 +1,5 @@
 """Both shipped neighbour-scan kernels -- k_scan_pw (scan_variant 4: persistent warps, TMA-fed double buffer,
-scan_pipe.cuh) and k_scan_ws (3: one CTA per 128-vertex tile) -- against the reference goldens and the C oracle,
+scan_pipe.cuh) and k_scan_ws (3: one CTA per 128-vertex tile), k_scan_pq (5: k_scan_pw with a per-warp ring of hard vertices) -- against the reference goldens and the C oracle,
 including the paths only unusual graphs reach: groups whose edges overflow one staging buffer (sub-ranges with
 synchronous bulk copies), vertices handed to the high-degree kernel, ragged last groups, weights."""
 import numpy as np
@@ -10,7 +10,7 @@ from test_gpu_parity import as_single, gpu, is_weighted, run_single  # noqa: F40
 
 pytestmark = pytest.mark.gpu
 EDGE = np.dtype([("tail", "<i8"), ("weight", "<f8")])
-VARIANTS = [3, 4]
+VARIANTS = [3, 4, 5]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

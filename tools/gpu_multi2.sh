@@ -5,8 +5,8 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 O=gpurun_out/m2
-timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_reference_main.py -x -q -m gpu -k "not eight_gpus" > ${O}_pytest.log 2>&1
-tail -n 12 ${O}_pytest.log
+timeout 2400 python -m pytest tests -q -m gpu -k "not eight_gpus" > ${O}_pytest.log 2>&1     # the WHOLE gpu suite, 2 GPUs visible
+tail -n 15 ${O}_pytest.log
 for mode in 1 0; do
   MVGPU_OPTIONS=comm_mode=$mode timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus 2 --steps 5 --warmup 3 > ${O}_bench_mode$mode.json 2> ${O}_bench_mode$mode.err
