@@ -134,6 +134,20 @@ int mvgpu_get_constant(mvgpu_ctx *ctx, double *out);
 int mvgpu_get_shard_info(mvgpu_ctx *ctx, int64_t *info6);
 
 /* ---- one-call form of the reference seam ------------------------------------------------------ */
+/* ---- the reference's USE_32_BIT_GRAPH build (utils.hpp:72-82: GraphElem = int32_t, GraphWeight = float) ------------
+ * A miniVite compiled with -DUSE_32_BIT_GRAPH holds int32 offsets and 8-byte {int32 tail_; float weight_} records
+ * (graph.hpp:60-66 with those types) and computes gains, 1/(2m) and the modularity in float.  These entry points take
+ * that build's arrays and reproduce that build's arithmetic: the gain is rounded where the float build rounds it
+ * (see gain_of in kernels.cuh), 1/(2m), the modularity and the exit test are evaluated in float (dspl.hpp:129,
+ * 447-448, 1401).  For unit-weight graphs whose integer sums stay below 2^24 every float sum of the reference is
+ * exact, and the results -- assignment, iteration count, modularity -- are bit-identical to the float build's;
+ * beyond that the float build is not reproducible against itself (its OpenMP reductions round in arbitrary order)
+ * and the comparison is by tolerance.  parts / edge_indices are int32 here, like every GraphElem of that build. */
+int mvgpu_upload_shard32(mvgpu_ctx *ctx, int32_t nv_global, const int32_t *parts, int32_t lnv, int32_t lne,
+                         const int32_t *edge_indices, const void *edge_list8);
+int mvgpu_louvain32(mvgpu_ctx *ctx, float lower, float thresh, int *iters, float *modularity);
+int mvgpu_get_communities32(mvgpu_ctx *ctx, int32_t *out);
+
 /* distLouvainMethod(me, nprocs, g, ..., lower, thresh, iters) for a single-GPU run with HOST arrays:
  * create + upload + louvain (+ optional assignment download into comm_out, may be NULL) + destroy. */
 int mvgpu_dist_louvain_method(int device, int64_t nv, int64_t ne_local, const int64_t *edge_indices,

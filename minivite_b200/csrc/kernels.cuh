@@ -82,6 +82,7 @@ struct ScanParams {
   const double *self_d;            // weighted: truncated self-loop weight (dspl.hpp:285)
   const double *vdeg;              // weighted: vertex degree (dspl.hpp:82-107)
   double constant;                 // 1/(2m) (dspl.hpp:129)
+  int f32;                         // emulate the reference's USE_32_BIT_GRAPH arithmetic in the gain (see gain_of)
   Acc *acc;
   // high-degree scratch
   const int32_t *heavy_list;
@@ -193,10 +194,17 @@ __device__ __forceinline__ unsigned long long pack_delta(int dsize, long long dd
 
 // dspl.hpp:212 with the reference's evaluation order and no FMA contraction:
 //   curGain = 2.0*(eiy-eix) - ((2.0*vDegree)*(ay-ax))*constant
-__device__ __forceinline__ double gain_of(double eiy, double eix, double vdeg, double ay, double ax, double c) {
-  const double t1 = __dmul_rn(2.0, __dsub_rn(eiy, eix));
-  const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), __dsub_rn(ay, ax)), c);
-  return __dsub_rn(t1, t2);
+// f32 = the reference's USE_32_BIT_GRAPH build (utils.hpp:72-82): GraphWeight is float there, so (eiy-eix) and (ay-ax)
+// are float subtractions, the 2.0 literals promote the rest to double, and the assignment to `GraphWeight curGain`
+// rounds the result to float.  The values handed in are exact integers (or doubles made from floats), so rounding the
+// two differences and the result to float reproduces that build's gain bit for bit.
+__device__ __forceinline__ double gain_of(double eiy, double eix, double vdeg, double ay, double ax, double c, int f32 = 0) {
+  double de = __dsub_rn(eiy, eix), da = __dsub_rn(ay, ax);
+  if (f32) { de = (double)__double2float_rn(de); da = (double)__double2float_rn(da); }
+  const double t1 = __dmul_rn(2.0, de);
+  const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), da), c);
+  const double g = __dsub_rn(t1, t2);
+  return f32 ? (double)__double2float_rn(g) : g;
 }
 
 // (gain, id) ordering of dspl.hpp:214-215: larger gain wins; equal non-zero gains -> smaller id (better_l below).
@@ -402,13 +410,13 @@ __global__ void __launch_bounds__(kTileV) k_scan_ws(const ScanParams p) {
       m = m2;
       if (has) {
         if (UNIT) sum1 = (double)c1;
-        const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant);
+        const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant, p.f32);
         if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
         if (ck2 >= 0) {
           double ay2;
           if (UNIT) { ay2 = (double)__ldg(at_cdeg<MULTI>(p, ck2)); sum2 = (double)c2; }
           else ay2 = __ldg(&at_cinfo_w<MULTI>(p, ck2)->degree);
-          const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant);
+          const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant, p.f32);
           if (better_l<MULTI>(p, g2, ck2, bg, best, lbest)) { bg = g2; best = ck2; }
         }
       }
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(256) k_scan_heavy(const ScanParams p) {
       const CommW cw = ptr_cinfo_w<MULTI>(p, yo)[yi];
       ysz = cw.size; ay = cw.degree; eiy = vd[i];
     }
-    const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant);
+    const double g = gain_of(eiy, eix, vdeg, ay, ax, p.constant, p.f32);
     if (better_l<MULTI>(p, g, y, bg, by, lby)) { bg = g; by = y; bsz = ysz; }
   }
   if (by != cc && lby == kNoLabel) lby = label_of<MULTI>(p, by);   // partial winners carry their label into the reduction
@@ -681,6 +689,19 @@ __global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long
 __global__ void __launch_bounds__(256) k_extract_weights(const Edge16 *edges, long long lne, double *weights) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x)
     weights[e] = __ldcs(&edges[e].weight);
+}
+
+// USE_32_BIT_GRAPH input ({int32 tail; float weight} records, int32 offsets) -> the 64-bit layout the setup kernels read
+struct Edge8 { int tail; float weight; };
+__global__ void __launch_bounds__(256) k_widen_shard32(const Edge8 *e8, long long lne, const int32_t *rp32, long long lnv,
+                                                       Edge16 *e16, long long *rp64) {
+  const long long gsz = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long e = t0; e < lne; e += gsz) {
+    const Edge8 x = e8[e];
+    Edge16 y; y.tail = x.tail; y.weight = (double)x.weight;
+    e16[e] = y;
+  }
+  for (long long i = t0; i <= lnv; i += gsz) rp64[i] = rp32[i];
 }
 
 __global__ void __launch_bounds__(256) k_fill_ones(double *w, long long n) {

@@ -182,6 +182,7 @@ struct mvgpu_ctx {
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
   bool unit = true;
+  bool f32 = false;                    // shard came through mvgpu_upload_shard32: float-build arithmetic (see mvgpu.h)
   double constant = 0.0;
   int32_t *d_final = nullptr;          // currComm at exit (points into comm_a/comm_b)
   bool final_ready = false;            // final_orig holds the assignment of the last run in the caller's numbering
@@ -743,6 +744,7 @@ int setup_run(mvgpu_ctx *c) {
   CK(cudaStreamSynchronize(s));
   if (c->nranks > 1 && c->hc.is_open()) c->hc.allreduce(&h.total_weight, 1, [](double a, double b) { return a + b; });
   c->constant = 1.0 / h.total_weight;
+  if (c->f32) c->constant = (double)(float)(1.0 / (double)(float)h.total_weight);   // dspl.hpp:129 with GraphWeight = float
   const int has_self = h.has_self ? 1 : 0;
   c->simple_sorted = c->unit && !h.unordered && !has_self;
   if (c->maxdeg > heavy_deg) {
@@ -813,7 +815,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   sp.cache_policy = c->opt_cache_policy;
   sp.relabel = c->relabel;
   sp.rowptr = c->a_rowptr; sp.tails = c->a_tails; sp.weights = c->unit ? nullptr : c->a_weights;
-  sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant;
+  sp.self_i = c->self_i.p; sp.self_d = c->self_d.p; sp.vdeg = c->vdeg.p; sp.constant = c->constant; sp.f32 = c->f32 ? 1 : 0;
   sp.heavy_list = c->heavy_list.p; sp.heavy_off = c->heavy_off.p; sp.hkeys = c->hkeys.p; sp.hvals_d = c->hvals_d.p; sp.hvals_i = c->hvals_i.p;
   sp.pt = c->pt;
   sp.loc_cdeg = c->cdeg.p; sp.loc_csize = c->csize.p; sp.loc_upd = c->upd.p; sp.loc_cinfo_w = c->cinfo_w.p;
@@ -834,7 +836,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     cudaEvent_t e0 = get_event(c, ev++), e1 = get_event(c, ev++), e2 = get_event(c, ev++), e3 = get_event(c, ev++);
     CK(cudaEventRecord(e0, s));
     // iteration 1 of a simple graph: every community is a singleton (scan_pipe.cuh, FIRST)
-    TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant >= 4));
+    TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant >= 4 && !c->f32));
     CK(cudaEventRecord(e1, s));
     const bool p2p = c->nranks > 1 && c->opt_comm_mode == 1;
     if (c->nranks > 1) {
@@ -891,16 +893,25 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     }
     // dspl.hpp:447-448
     const double cst = c->constant;
+    if (c->f32) {                      // GraphWeight = float: every product and the difference round to float
+      const float cf = (float)cst;
+      volatile float t1f = (float)e_xx * cf;
+      volatile float t2af = (float)a2_x * cf;
+      volatile float t2f = t2af * cf;
+      volatile float df = t1f - t2f;
+      currMod = (double)std::fabs(df);
+    } else {
     volatile double term1 = e_xx * cst;
     volatile double term2a = a2_x * cst;
     volatile double term2 = term2a * cst;
     currMod = std::fabs(term1 - term2);
+    }
     if (c->opt_trace) {
       mvgpu_iter_trace t;
       t.modularity = currMod; t.moved = (int64_t)moved; t.chash = hash;
       c->trace.push_back(t);
     }
-    if (currMod - prevMod < thresh) break;                     // dspl.hpp:1401-1402
+    if (c->f32 ? ((float)currMod - (float)prevMod < (float)thresh) : (currMod - prevMod < thresh)) break;   // dspl.hpp:1401-1402
     prevMod = currMod;
     if (prevMod < lower) prevMod = lower;                      // dspl.hpp:1404-1406
     std::swap(cur, tgt);                                       // rotation (dspl.hpp:1408-1422) is a pointer swap
@@ -1194,6 +1205,7 @@ int mvgpu_upload_shard(mvgpu_ctx *c, int64_t nv_global, const int64_t *parts, in
   if (!c || !parts || !edge_indices || (lne && !edge_list)) return fail("null argument");
   CK(cudaSetDevice(c->device));
   TRY(set_graph(c, nv_global, parts, lnv, lne));
+  c->f32 = false;
   TRY(c->in_rowptr.ensure(lnv + 1));
   cudaEvent_t a = get_event(c, 0), b = get_event(c, 1);
   CK(cudaEventRecord(a, c->stream));
@@ -1228,6 +1240,7 @@ int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *pa
   if (((uintptr_t)d_edge_list & 15) || ((uintptr_t)d_edge_indices & 7)) return fail("device arrays must be 16/8-byte aligned");
   CK(cudaSetDevice(c->device));
   TRY(set_graph(c, nv_global, parts, lnv, lne));
+  c->f32 = false;
   c->d_rowptr64 = reinterpret_cast<const long long *>(d_edge_indices);
   c->d_edges = reinterpret_cast<const Edge16 *>(d_edge_list);
   c->d_tails32 = nullptr;
@@ -1338,6 +1351,7 @@ int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *c, int64_t nv_global, int unit_weight
   std::vector<int64_t> parts(p + 1);
   for (int q = 0; q <= p; q++) parts[q] = (nv_global * q) / p;
   TRY(set_graph(c, nv_global, parts.data(), P.n, lne));
+  c->f32 = false;
   c->d_rowptr64 = c->gen_rowptr.p;
   c->d_edges = c->gen_edges.p;
   c->d_tails32 = nullptr;
@@ -1463,6 +1477,54 @@ int mvgpu_get_constant(mvgpu_ctx *c, double *out) {
 int mvgpu_get_shard_info(mvgpu_ctx *c, int64_t *info6) {
   if (!c || !info6) return fail("null argument");
   info6[0] = c->lnv; info6[1] = c->lne; info6[2] = c->nghost; info6[3] = c->nsend; info6[4] = c->nheavy; info6[5] = c->maxdeg;
+  return 0;
+}
+
+// ---- USE_32_BIT_GRAPH surface (utils.hpp:72-82): int32 offsets, {int32 tail; float weight} records, float results ----
+int mvgpu_upload_shard32(mvgpu_ctx *c, int32_t nv_global, const int32_t *parts, int32_t lnv, int32_t lne,
+                         const int32_t *edge_indices, const void *edge_list8) {
+  if (!c || !parts || !edge_indices || (lne && !edge_list8)) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  std::vector<int64_t> parts64(parts, parts + c->nranks + 1);
+  TRY(set_graph(c, nv_global, parts64.data(), lnv, lne));
+  c->f32 = true;
+  DevBuf<Edge8> e8;
+  DevBuf<int32_t> rp32;
+  TRY(e8.ensure((size_t)lne)); TRY(rp32.ensure((size_t)lnv + 1));
+  TRY(c->in_edges.ensure(lne)); TRY(c->in_rowptr.ensure(lnv + 1));
+  cudaEvent_t a = get_event(c, 0), b = get_event(c, 1);
+  CK(cudaEventRecord(a, c->stream));
+  CK(cudaMemcpyAsync(rp32.p, edge_indices, sizeof(int32_t) * ((size_t)lnv + 1), cudaMemcpyHostToDevice, c->stream));
+  if (lne) CK(cudaMemcpyAsync(e8.p, edge_list8, sizeof(Edge8) * (size_t)lne, cudaMemcpyHostToDevice, c->stream));
+  k_widen_shard32<<<grid_for(std::max<long long>(lne, lnv + 1), 256, c->num_sms, 16), 256, 0, c->stream>>>(e8.p, lne, rp32.p, lnv, c->in_edges.p,
+                                                                                                      c->in_rowptr.p);
+  CK(cudaEventRecord(b, c->stream));
+  CK(cudaEventSynchronize(b));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  c->h2d_s = ms * 1e-3;
+  c->h2d_bytes = (long long)sizeof(int32_t) * (lnv + 1) + (long long)sizeof(Edge8) * lne;
+  c->d_rowptr64 = c->in_rowptr.p;
+  c->d_edges = c->in_edges.p;
+  c->d_tails32 = nullptr;
+  return 0;
+}
+
+int mvgpu_louvain32(mvgpu_ctx *c, float lower, float thresh, int *iters, float *modularity) {
+  if (!c || !iters || !modularity) return fail("null argument");
+  if (!c->f32) return fail("mvgpu_louvain32 needs a shard uploaded with mvgpu_upload_shard32");
+  double mod = 0.0;
+  TRY(run_louvain(c, (double)lower, (double)thresh, iters, &mod));
+  *modularity = (float)mod;
+  return 0;
+}
+
+int mvgpu_get_communities32(mvgpu_ctx *c, int32_t *out) {
+  if (!c || !c->d_final) return fail("no result yet");
+  if (c->lnv == 0) return 0;
+  TRY(final_in_caller_order(c));
+  CK(cudaMemcpyAsync(out, c->final_orig.p, sizeof(int32_t) * c->lnv, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

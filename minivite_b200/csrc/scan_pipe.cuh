@@ -260,14 +260,14 @@ k_scan_pw(const ScanParams p, int ngroups) {
         for (int k = 0; k < d; k++) amin = min(amin, sc[o0 + k]);
         if (d) {
           const double dd = (double)d;
-          const double gmax = gain_of(1.0, 0.0, dd, (double)amin, 0.0, p.constant);
-          const double gnext = gain_of(1.0, 0.0, dd, (double)amin + 1.0, 0.0, p.constant);
+          const double gmax = gain_of(1.0, 0.0, dd, (double)amin, 0.0, p.constant, p.f32);
+          const double gnext = gain_of(1.0, 0.0, dd, (double)amin + 1.0, 0.0, p.constant, p.f32);
           if (gmax > 0.0) {                                   // maxGain starts at 0: only a positive gain moves (dspl.hpp:214)
             const bool collide = !(gnext < gmax);             // never seen: two degrees rounding to one gain -> compare gains
             int by = cc, lb = 0x7fffffff;
             for (int k = 0; k < d; k++) {
               const int a = sc[o0 + k];
-              if (a == amin || (collide && gain_of(1.0, 0.0, dd, (double)a, 0.0, p.constant) == gmax)) {
+              if (a == amin || (collide && gain_of(1.0, 0.0, dd, (double)a, 0.0, p.constant, p.f32) == gmax)) {
                 const int tl = __ldg(p.tails + ra + k);
                 const int y = (!MULTI || tl < p.lnv) ? (int)p.base + tl : __ldg(p.cur + tl);
                 const int ly = label_of<MULTI>(p, y);
@@ -326,13 +326,13 @@ k_scan_pw(const ScanParams p, int ngroups) {
         m = m2;
         if (has) {
           if (UNIT) sum1 = (double)c1;
-          const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant);
+          const double g1 = gain_of(sum1, eix, vdeg, ay1, ax, p.constant, p.f32);
           if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
           if (ck2 >= 0) {
             double ay2;
             if (UNIT) { ay2 = (double)__ldg(at_cdeg<MULTI>(p, ck2)); sum2 = (double)c2; }
             else ay2 = __ldg(&at_cinfo_w<MULTI>(p, ck2)->degree);
-            const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant);
+            const double g2 = gain_of(sum2, eix, vdeg, ay2, ax, p.constant, p.f32);
             if (better_l<MULTI>(p, g2, ck2, bg, best, lbest)) { bg = g2; best = ck2; }
           }
         }

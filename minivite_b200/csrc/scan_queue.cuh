@@ -26,9 +26,6 @@ namespace mv {
 #ifndef MV_Q_ENT
 #define MV_Q_ENT 12                    // leftover communities a ring slot holds
 #endif
-#ifndef MV_PASS0_ASM
-#define MV_PASS0_ASM 0
-#endif
 #ifndef MV_Q_SLOTS
 #define MV_Q_SLOTS 64                   // ring slots per warp: up to (drain threshold - 1) waiting + 32 from one group
 #endif
@@ -95,7 +92,10 @@ __global__ void __launch_bounds__(kPwWarps * 32, MV_PW_RES_WARPS / kPwWarps) k_s
   };
   // pass 1 + decision for one vertex whose leftover communities sit in seg[0..m): two communities per round, exactly
   // k_scan_pw's loop.  Lanes without work pass m = 0.  Returns the chosen community.
-  auto pass1 = [&](int32_t *seg, int m, int cc, double eix, double vdeg, double ax) -> int {
+  // A candidate that holds c of the vertex's edges cannot reach more than fl(2 (c - e_ix) + gB), gB = fl(fl(fl(2 k_i) a_x) c)
+  // (same monotonicity argument as for the vertex-level bound): if that is below the best gain so far the exact gain
+  // is not evaluated.
+  auto pass1 = [&](int32_t *seg, int m, int cc, double eix, double vdeg, double ax, double gB) -> int {
     int best = cc, lbest = kNoLabel;
     double bg = 0.0;
     for (;;) {
@@ -116,11 +116,13 @@ __global__ void __launch_bounds__(kPwWarps * 32, MV_PW_RES_WARPS / kPwWarps) k_s
       }
       m = m2;
       if (has) {
-        const double g1 = gain_of((double)c1, eix, vdeg, ay1, ax, p.constant);
-        if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
-        if (ck2 >= 0) {
+        if (p.f32 || !(__dadd_rn(__dmul_rn(2.0, __dsub_rn((double)c1, eix)), gB) < bg)) {
+          const double g1 = gain_of((double)c1, eix, vdeg, ay1, ax, p.constant, p.f32);
+          if (better_l<MULTI>(p, g1, ck1, bg, best, lbest)) { bg = g1; best = ck1; }
+        }
+        if (ck2 >= 0 && (p.f32 || !(__dadd_rn(__dmul_rn(2.0, __dsub_rn((double)c2, eix)), gB) < bg))) {
           const double ay2 = (double)__ldg(at_cdeg<MULTI>(p, ck2));
-          const double g2 = gain_of((double)c2, eix, vdeg, ay2, ax, p.constant);
+          const double g2 = gain_of((double)c2, eix, vdeg, ay2, ax, p.constant, p.f32);
           if (better_l<MULTI>(p, g2, ck2, bg, best, lbest)) { bg = g2; best = ck2; }
         }
       }
@@ -145,7 +147,8 @@ __global__ void __launch_bounds__(kPwWarps * 32, MV_PW_RES_WARPS / kPwWarps) k_s
     const int m = on ? (h.z & 0xffff) : 0, d = h.z >> 16;
     const double vdeg = (double)d, sl = (on && p.has_self) ? (double)__ldg(p.self_i + h.x) : 0.0;
     const double eix = __dsub_rn((double)(d - m), sl), ax = __dsub_rn((double)(unsigned int)h.w, vdeg);
-    const int best = pass1(q_ent + slot * kQEnt, m, h.y, eix, vdeg, ax);
+    const double gB = __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), ax), p.constant);
+    const int best = pass1(q_ent + slot * kQEnt, m, h.y, eix, vdeg, ax, gB);
     if (on) finish(h.x, h.y, best, d);
     qhead = (qhead + n) % kQSlots;
     qcount -= n;
@@ -244,35 +247,22 @@ __global__ void __launch_bounds__(kPwWarps * 32, MV_PW_RES_WARPS / kPwWarps) k_s
       // ---- pass 0 (counter[0], dspl.hpp:312-318): count the own community, compact the others to the front
       int32_t *const seg = sc + o0;
       int m = 0;
-#if MV_PASS0_ASM
-      {   // read / write positions as 32-bit shared-window addresses: load, compare, predicated store + increment
-        uint32_t rp = smem_u32(seg), wp = rp;
-        const uint32_t w0 = wp;
-        for (int k = 0; k < d; k++, rp += 4) {
-          int x;
-          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(x) : "r"(rp));
-          if (x != cc) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(wp), "r"(x) : "memory"); wp += 4; }
-        }
-        m = (int)((wp - w0) >> 2);
-      }
-#else
       for (int k = 0; k < d; k++) {
         const int x = seg[k];
         if (x != cc) { seg[m] = x; m++; }
       }
-#endif
       if (d) acc_le_u += (unsigned long long)(d - m);
       const double vdeg = (double)d;
       const double eix = __dsub_rn((double)(d - m), sl), ax = __dsub_rn((double)cc_deg_u, vdeg);
       // ---- can any candidate beat maxGain = 0?  (see the header: exact upper bound on curGain)
-      const double bound = __dadd_rn(__dmul_rn(2.0, __dsub_rn((double)m, eix)),
-                                     __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), ax), p.constant));
-      const bool hard = m > 0 && !(bound <= 0.0);
+      const double gB = __dmul_rn(__dmul_rn(__dmul_rn(2.0, vdeg), ax), p.constant);
+      const double bound = __dadd_rn(__dmul_rn(2.0, __dsub_rn((double)m, eix)), gB);
+      const bool hard = m > 0 && (p.f32 || !(bound <= 0.0));    // the bounds are derived for the double-precision gain
       const uint32_t hmask = __ballot_sync(0xffffffffu, hard);
       const bool in_place = __any_sync(0xffffffffu, hard && m > kQEnt);
       if (in_place) {
         // early iterations: long leftover lists everywhere -> pass 1 where the lists are, like k_scan_pw
-        const int best = pass1(seg, hard ? m : 0, cc, eix, vdeg, ax);
+        const int best = pass1(seg, hard ? m : 0, cc, eix, vdeg, ax, gB);
         if (mine) finish(v, cc, best, d);
       } else {
         if (mine && !hard) finish(v, cc, cc, d);

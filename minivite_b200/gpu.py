@@ -29,7 +29,7 @@ class Timings(ctypes.Structure):
 EXPORTS = ["mvgpu_last_error", "mvgpu_device_count", "mvgpu_create", "mvgpu_destroy", "mvgpu_get_unique_id",
            "mvgpu_comm_init", "mvgpu_upload_shard", "mvgpu_attach_shard_device", "mvgpu_generate_rgg_shard", "mvgpu_generate_rgg_shard_ex",
            "mvgpu_download_shard", "mvgpu_louvain",
-           "mvgpu_get_communities", "mvgpu_get_communities_device", "mvgpu_set_option", "mvgpu_get_trace",
+           "mvgpu_get_communities", "mvgpu_get_communities_device", "mvgpu_upload_shard32", "mvgpu_louvain32", "mvgpu_get_communities32", "mvgpu_set_option", "mvgpu_get_trace",
            "mvgpu_get_timings", "mvgpu_get_scan_times", "mvgpu_get_constant", "mvgpu_get_shard_info", "mvgpu_dist_louvain_method"]
 
 _lib = None
@@ -56,6 +56,9 @@ def lib():
         L.mvgpu_download_shard.argtypes = [vp, vp, vp]
         L.mvgpu_louvain.argtypes = [vp, dbl, dbl, ctypes.POINTER(ci), ctypes.POINTER(dbl)]
         L.mvgpu_get_communities.argtypes = [vp, vp]
+        L.mvgpu_upload_shard32.argtypes = [vp, ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]
+        L.mvgpu_louvain32.argtypes = [vp, ctypes.c_float, ctypes.c_float, ctypes.POINTER(ci), ctypes.POINTER(ctypes.c_float)]
+        L.mvgpu_get_communities32.argtypes = [vp, vp]
         L.mvgpu_get_communities_device.argtypes = [vp, ctypes.POINTER(vp)]
         L.mvgpu_set_option.argtypes = [vp, ctypes.c_char_p, i64]
         L.mvgpu_get_trace.argtypes = [vp, ci, vp, ctypes.POINTER(ci)]
@@ -116,6 +119,29 @@ class LouvainGPU:
         _ck(lib().mvgpu_upload_shard(self._h, int(nv_global), parts.ctypes.data, lnv, lne, rowptr.ctypes.data,
                                      edges.ctypes.data if lne else None))
         self.lnv = lnv
+
+    # ---- the reference's USE_32_BIT_GRAPH build: int32 ids, float weights, float results (include/mvgpu.h)
+    def upload32(self, nv_global, parts, rowptr, edges):
+        parts = np.ascontiguousarray(parts, dtype=np.int32)
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+        edges = np.ascontiguousarray(edges)
+        assert edges.dtype.itemsize == 8, "edge records must be {int32 tail; float weight}"
+        lnv, lne = len(rowptr) - 1, len(edges)
+        assert int(rowptr[-1]) == lne
+        _ck(lib().mvgpu_upload_shard32(self._h, int(nv_global), parts.ctypes.data, lnv, lne, rowptr.ctypes.data,
+                                       edges.ctypes.data if lne else None))
+        self.lnv = lnv
+
+    def louvain32(self, lower=-1.0, thresh=1.0e-6):
+        iters = ctypes.c_int(0)
+        mod = ctypes.c_float(0.0)
+        _ck(lib().mvgpu_louvain32(self._h, lower, thresh, ctypes.byref(iters), ctypes.byref(mod)))
+        return mod.value, iters.value
+
+    def communities32(self):
+        out = np.empty(self.lnv, dtype=np.int32)
+        _ck(lib().mvgpu_get_communities32(self._h, out.ctypes.data))
+        return out
 
     def attach_device(self, nv_global, parts, lnv, lne, d_rowptr_ptr, d_edges_ptr, keepalive=None):
         """Arrays already resident in this GPU's memory (raw device pointers)."""

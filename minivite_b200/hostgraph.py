@@ -151,3 +151,20 @@ def write_graph_arrays(path, nv, rowptr, tails, weights=None):
         f.write(np.array([nv, ne], dtype=np.int64).tobytes())
         f.write(rowptr.tobytes())
         f.write(e.tobytes())
+
+
+EDGE32_DTYPE = np.dtype([("tail", "<i4"), ("weight", "<f4")])
+
+
+def write_graph_arrays32(path, nv, rowptr, tails, weights=None):
+    """Same file for a miniVite compiled with -DUSE_32_BIT_GRAPH (utils.hpp:72-82): every GraphElem is int32, every
+    GraphWeight float -- header {int32 nv; int32 ne}, int32 offsets, {int32 tail; float weight} records."""
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    ne = int(rowptr[-1])
+    e = np.zeros(ne, EDGE32_DTYPE)
+    e["tail"] = tails
+    e["weight"] = 1.0 if weights is None else weights
+    with open(path, "wb") as f:
+        f.write(np.array([nv, ne], dtype=np.int32).tobytes())
+        f.write(rowptr.tobytes())
+        f.write(e.tobytes())

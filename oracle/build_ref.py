@@ -20,6 +20,9 @@ Hooks (all on stderr / side files, all off unless the env var is set):
   always              rank 0 prints ``RESULT mod=%.17g iters=%d time=%.9g nv=%ld ne=%ld nprocs=%d``
                       to stderr next to the reference's own report block (main.cpp:178)
 
+``oracle/_ref/miniVite_ref32`` is the same source tree compiled with the reference's own ``-DUSE_32_BIT_GRAPH``
+(utils.hpp:72-82); it pins the ``mvgpu_*32`` entry points (tests/golden/make_golden_32.py).
+
 ``--gpu`` additionally builds ``oracle/_ref/miniVite_ref_gpu``: the reference's own ``main.cpp`` with the patch of
 INTEGRATION.md section 2 applied (the ``distLouvainMethod`` call replaced by ``mvgpu_upload_shard`` +
 ``mvgpu_louvain`` through the C ABI, everything else -- command line, graph construction, timer brackets, report --
@@ -47,14 +50,14 @@ static inline unsigned long long mv_vhash(long long gid, long long val) {
 }
 """
 
-HOOK_ITER = r"""    if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; GraphElem mv = 0, mvg = 0;
+HOOK_ITER = r"""    if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; long long mv = 0, mvg = 0;
       for (GraphElem i = 0; i < nv; i++) { hl += mv_vhash(i + base, targetComm[i]); mv += (targetComm[i] != currComm[i]); }
       MPI_Allreduce(&hl, &hg, 1, MPI_INT64_T, MPI_SUM, gcomm); MPI_Allreduce(&mv, &mvg, 1, MPI_INT64_T, MPI_SUM, gcomm);
       if (me == 0) fprintf(stderr, "ITER %d mod=%.17g moved=%ld chash=%016llx\n", numIters, currMod, (long)mvg, hg); }
 """
 
 HOOK_FINAL = r"""  iters = numIters;
-  if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; GraphElem nc = 0, ncg = 0;
+  if (getenv("MV_TRACE")) { unsigned long long hl = 0, hg = 0; long long nc = 0, ncg = 0;
     for (GraphElem i = 0; i < nv; i++) { hl += mv_vhash(i + base, currComm[i]); }
     for (GraphElem i = 0; i < nv; i++) { nc += (localCinfo[i].size > 0); }
     MPI_Allreduce(&hl, &hg, 1, MPI_INT64_T, MPI_SUM, gcomm); MPI_Allreduce(&nc, &ncg, 1, MPI_INT64_T, MPI_SUM, gcomm);
@@ -151,9 +154,11 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--gpu", action="store_true", help="also build miniVite_ref_gpu (reference main.cpp + INTEGRATION.md patch)")
+    ap.add_argument("--no32", action="store_true", help="skip miniVite_ref32 (the reference compiled with -DUSE_32_BIT_GRAPH)")
     args = ap.parse_args()
     out_bin = os.path.join(OUT_DIR, "miniVite_ref")
     gpu_bin = os.path.join(OUT_DIR, "miniVite_ref_gpu")
+    bin32 = os.path.join(OUT_DIR, "miniVite_ref32")
     repo = os.path.dirname(HERE)
     libdir = os.path.join(repo, "minivite_b200", "lib")
     if not os.path.isdir(args.ref):
@@ -166,7 +171,8 @@ def main():
     stamp = max(os.path.getmtime(p) for p in srcs + [__file__, os.path.join(SHIM_DIR, "mpi.h")])
     want_gpu = args.gpu and os.path.exists(os.path.join(libdir, "libmvgpu.so"))
     gpu_stamp = max(stamp, os.path.getmtime(os.path.join(repo, "include", "mvgpu.h")))
-    cpu_fresh = os.path.exists(out_bin) and os.path.getmtime(out_bin) >= stamp
+    cpu_fresh = os.path.exists(out_bin) and os.path.getmtime(out_bin) >= stamp and (
+        args.no32 or (os.path.exists(bin32) and os.path.getmtime(bin32) >= stamp))
     gpu_fresh = not want_gpu or (os.path.exists(gpu_bin) and os.path.getmtime(gpu_bin) >= gpu_stamp)
     if not args.force and cpu_fresh and gpu_fresh:
         print(f"build_ref: {out_bin} up to date")
@@ -192,6 +198,11 @@ def main():
                "-I", SHIM_DIR, "-I", tmp, os.path.join(tmp, "main.cpp"), "-o", out_bin]
         print("build_ref:", " ".join(cmd))
         subprocess.check_call(cmd)
+        if not args.no32:
+            # the same sources with the reference's own 32-bit switch (utils.hpp:72-82: int32 ids, float weights)
+            cmd32 = cmd[:5] + ["-DUSE_32_BIT_GRAPH"] + cmd[5:-1] + [bin32]
+            print("build_ref:", " ".join(cmd32))
+            subprocess.check_call(cmd32)
         if want_gpu:
             open(os.path.join(tmp, "main_gpu.cpp"), "w").write(patch_main_for_gpu(m))
             cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-DPRINT_DIST_STATS",

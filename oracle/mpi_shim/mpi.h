@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,11 +57,12 @@ enum {
 
 namespace mvshim {
 
+static size_t g_struct_bytes = 24;   // extent of the one struct type the reference creates (set by MPI_Type_create_struct)
 static inline size_t type_size(MPI_Datatype t) {
   switch (t) {
     case MPI_BYTE: return 1;
     case MPI_INT: case MPI_FLOAT: case MPI_INT32_T: return 4;
-    case MVSHIM_STRUCT24: return 24;
+    case MVSHIM_STRUCT24: return g_struct_bytes;
     default: return 8;
   }
 }
@@ -290,8 +292,17 @@ static inline int MPI_Finalize() {
   return 0;
 }
 static inline int MPI_Get_address(const void *p, MPI_Aint *a) { *a = (MPI_Aint)p; return 0; }
-static inline int MPI_Type_create_struct(int, const int *, const MPI_Aint *, const MPI_Datatype *, MPI_Datatype *t) {
-  *t = MVSHIM_STRUCT24;   // the only struct type the reference creates: CommInfo {int64,int64,double}
+static inline int MPI_Type_create_struct(int n, const int *blens, const MPI_Aint *displ, const MPI_Datatype *types, MPI_Datatype *t) {
+  // the only struct type the reference creates is CommInfo {GraphElem, GraphElem, GraphWeight}: 24 bytes in the default
+  // build, 12 with -DUSE_32_BIT_GRAPH.  Extent = end of the last member, rounded up to the widest member.
+  size_t end = 0, align = 1;
+  for (int i = 0; i < n; i++) {
+    const size_t sz = mvshim::type_size(types[i]);
+    end = std::max(end, (size_t)displ[i] + sz * (size_t)blens[i]);
+    align = std::max(align, sz);
+  }
+  mvshim::g_struct_bytes = (end + align - 1) / align * align;
+  *t = MVSHIM_STRUCT24;
   return 0;
 }
 static inline int MPI_Type_commit(MPI_Datatype *) { return 0; }

@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "louvain_oracle.c")
 LIB = os.path.join(HERE, "_build", "liblouvain_oracle.so")
 REF_BIN = os.path.join(HERE, "_ref", "miniVite_ref")
+REF32_BIN = os.path.join(HERE, "_ref", "miniVite_ref32")       # the reference compiled with -DUSE_32_BIT_GRAPH
 REF_GPU_BIN = os.path.join(HERE, "_ref", "miniVite_ref_gpu")   # reference main.cpp + INTEGRATION.md patch (build_ref.py --gpu)
 
 TRACE_DTYPE = np.dtype([("modularity", "<f8"), ("moved", "<i8"), ("chash", "<u8")])
@@ -136,11 +137,13 @@ def run_reference(args, nranks=1, threads=1, trace=True, dump_comm=None, dump_gr
     return out
 
 
-def read_comm_dump(prefix, nranks):
-    """currComm slices written by MV_DUMP_COMM; returns list of (base, int64 array)."""
+def read_comm_dump(prefix, nranks, elem=np.int64):
+    """currComm slices written by MV_DUMP_COMM (16-byte header, then GraphElem entries: int64, or int32 for the
+    USE_32_BIT_GRAPH build); returns list of (base, int64 array)."""
     out = []
     for r in range(nranks):
-        raw = np.fromfile(f"{prefix}.{r}", dtype=np.int64)
-        base, nv = int(raw[0]), int(raw[1])
-        out.append((base, raw[2:2 + nv].copy()))
+        hdr = np.fromfile(f"{prefix}.{r}", dtype=np.int64, count=2)
+        base, nv = int(hdr[0]), int(hdr[1])
+        body = np.fromfile(f"{prefix}.{r}", dtype=elem, offset=16, count=nv)
+        out.append((base, body.astype(np.int64)))
     return out
