@@ -162,6 +162,7 @@ struct mvgpu_ctx {
   DevBuf<unsigned long long> heavy_off;
   long long nheavy = 0, maxdeg = 0;
   int scan_has_self = 0, scan_heavy_deg = kECap;
+  int scan_kernel = 4;                 // the persistent kernel this iteration runs: 4 = k_scan_pw, 5 = k_scan_pq (see run_louvain)
   bool simple_sorted = false;          // unit graph, adjacency lists strictly increasing (no parallel edges), no self loops
   // peers
   DevBuf<P2PState> p2p;
@@ -177,7 +178,7 @@ struct mvgpu_ctx {
   void *last_ptrs[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   unsigned last_gens[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // options
-  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 5, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
+  int opt_trace = 0, opt_force_weighted = 0, opt_scan_variant = 6, opt_cache_policy = 5, opt_reorder = 2, opt_region = 512, opt_comm_mode = 1, opt_compact_upload = 0, opt_host_threads = 8, opt_first_iter = 1, opt_host_transport = 0;
   long long opt_upload_chunk = 4LL << 20;
   long long opt_max_iters = 10000, opt_force_heavy_deg = 0;
   // results
@@ -403,7 +404,7 @@ int launch_scan_t(mvgpu_ctx *c, const ScanParams &sp, bool first) {
     attr_done = true;
   }
   const int tiles = (int)((c->lnv + kTileV - 1) / kTileV);
-  if (tiles > 0 && c->opt_scan_variant == 5 && UNIT && !first) {
+  if (tiles > 0 && c->opt_scan_variant >= 5 && c->scan_kernel == 5 && UNIT && !first) {
     // k_scan_pw's pipeline with a per-warp ring of hard vertices (scan_queue.cuh); iteration 1 and the weighted path
     // stay with k_scan_pw
     static int pq_ctas_per_sm = 0;
@@ -826,7 +827,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
   HostMail *mail = reinterpret_cast<HostMail *>(c->h_pin);
   const size_t ev_iter0 = ev;
   double prevMod = lower, currMod = -1.0;
-  int numIters = 0;
+  int numIters = 0, auto_choice = 4;
   const int fold_grid = grid_for(c->lnv, 256, c->num_sms, 8);
   for (;;) {                                                   // dspl.hpp:1338
     if (numIters >= c->opt_max_iters) return fail("max_iters reached without convergence");
@@ -836,6 +837,15 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     cudaEvent_t e0 = get_event(c, ev++), e1 = get_event(c, ev++), e2 = get_event(c, ev++), e3 = get_event(c, ev++);
     CK(cudaEventRecord(e0, s));
     // iteration 1 of a simple graph: every community is a singleton (scan_pipe.cuh, FIRST)
+    // Which persistent kernel?  k_scan_pq wins where the gathers hit L1 (RGG: 0.49 vs 0.60 ms per launch) and loses
+    // badly where they do not (its single tail buffer exposes the bulk-copy latency: -p 2 graph, 1.40 vs 0.80 ms), so
+    // scan_variant 6 (default) measures: iterations 2-4 and 6 run k_scan_pw, iteration 5 k_scan_pq, and from iteration 7
+    // on the kernel that was faster than the mean of its two neighbours runs.  Results are identical either way.
+    c->scan_kernel = c->opt_scan_variant == 5 ? 5 : 4;
+    if (c->opt_scan_variant == 6) {
+      if (numIters == 5) c->scan_kernel = 5;
+      else if (numIters >= 7) c->scan_kernel = auto_choice;
+    }
     TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant >= 4 && !c->f32));
     CK(cudaEventRecord(e1, s));
     const bool p2p = c->nranks > 1 && c->opt_comm_mode == 1;
@@ -890,6 +900,14 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       e_xx = c->unit ? (double)mail->acc.le_u : mail->acc.le_d;
       a2_x = c->unit ? (double)mail->acc.la2_u : mail->acc.la2_d;
       moved = mail->acc.moved; hash = mail->acc.hash;
+    }
+    if (c->opt_scan_variant == 6 && numIters == 6) {           // iterations 4..6 have completed (the stream was just synchronised)
+      float t4 = 0, t5 = 0, t6 = 0;
+      CK(cudaEventElapsedTime(&t4, c->events[ev_iter0 + 4 * 3], c->events[ev_iter0 + 4 * 3 + 1]));
+      CK(cudaEventElapsedTime(&t5, c->events[ev_iter0 + 4 * 4], c->events[ev_iter0 + 4 * 4 + 1]));
+      CK(cudaEventElapsedTime(&t6, c->events[ev_iter0 + 4 * 5], c->events[ev_iter0 + 4 * 5 + 1]));
+      auto_choice = (t5 < 0.5f * (t4 + t6)) ? 5 : 4;
+      c->tm.scan_kernel_chosen = auto_choice;
     }
     // dspl.hpp:447-448
     const double cst = c->constant;
@@ -1432,7 +1450,7 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "max_iters") { if (value < 1) return fail("max_iters < 1"); c->opt_max_iters = value; }
   else if (n == "force_weighted") c->opt_force_weighted = value != 0;
   else if (n == "force_heavy_deg") c->opt_force_heavy_deg = value;
-  else if (n == "scan_variant") { if (value < 3 || value > 5) return fail("scan_variant must be 5 (k_scan_pq, default), 4 (k_scan_pw) or 3 (k_scan_ws)"); c->opt_scan_variant = (int)value; }
+  else if (n == "scan_variant") { if (value < 3 || value > 6) return fail("scan_variant must be 6 (measure and choose, default), 5 (k_scan_pq), 4 (k_scan_pw) or 3 (k_scan_ws)"); c->opt_scan_variant = (int)value; }
   else if (n == "cache_policy") c->opt_cache_policy = (int)value;
   else if (n == "reorder") c->opt_reorder = (int)value;
   else if (n == "comm_mode") c->opt_comm_mode = (int)value;

@@ -20,7 +20,7 @@ class Timings(ctypes.Structure):
                 ("fold_s", ctypes.c_double), ("exchange_s", ctypes.c_double), ("h2d_s", ctypes.c_double),
                 ("scan_launches", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
                 ("iters", ctypes.c_int32), ("unit_weight", ctypes.c_int32), ("reorder_s", ctypes.c_double),
-                ("reordered", ctypes.c_int32), ("pad_", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64)]
+                ("reordered", ctypes.c_int32), ("scan_kernel_chosen", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -68,19 +68,31 @@ def run32(case, **opts):
 
 
 def test_float_build_unit_weight_cases_are_bit_exact(golden32):
+    """Decisions are exact: iteration count, moved counts, community hashes of every iteration and the final assignment
+    equal the float build's.  The float modularity is compared bit for bit where the float build's own sum of squared
+    degrees is exact (sum < 2^24: the n = 16 384 cases and the hand-made graphs) and within 4 float ulps beyond (the
+    reference adds squares sequentially in float there; this build adds exact integers and rounds once)."""
     n = 0
     for name, case in golden32.items():
         if case.get("unit_weight") is False or "weighted" in name:
             continue
-        for opts in ({}, {"scan_variant": 4}, {"scan_variant": 3}, {"reorder": 1, "region_size": 64}):
+        exact_mod = case["nv"] <= 16384
+        for opts in ({}, {"scan_variant": 5}, {"scan_variant": 4}, {"scan_variant": 3}, {"reorder": 1, "region_size": 64}):
             res = run32(case, **opts)
             assert res["unit"] == 1, name
-            # modularity: the golden is a float printed with 17 digits
-            assert np.float32(res["mod"]) == np.float32(float(case["modularity"])), (name, opts, res["mod"], case["modularity"])
-            trace = [{"modularity": float(np.float32(t["modularity"])), "moved": t["moved"], "chash": t["chash"]} for t in res["trace"]]
-            gold = dict(case, modularity=repr(float(np.float32(float(case["modularity"])))),
-                        trace=[dict(t, modularity=repr(float(np.float32(float(t["modularity"]))))) for t in case["trace"]])
-            assert_trace_matches(gold, res["iters"], float(np.float32(res["mod"])), trace, None, res["comm"] if "comm" in case else None)
+            assert res["iters"] == case["iters"], (name, opts)
+            mods = [(np.float32(res["mod"]), np.float32(float(case["modularity"])))]
+            assert len(res["trace"]) == len(case["trace"])
+            for t, g in zip(res["trace"], case["trace"]):
+                assert int(t["moved"]) == g["moved"] and int(t["chash"]) == int(g["chash"], 16), (name, opts)
+                mods.append((np.float32(t["modularity"]), np.float32(float(g["modularity"]))))
+            for a, b in mods:
+                if exact_mod:
+                    assert a == b, (name, opts, a, b)
+                else:
+                    assert abs(float(a) - float(b)) <= 4 * float(np.spacing(np.float32(abs(b)))), (name, opts, a, b)
+            if "comm" in case:
+                assert [int(x) for x in res["comm"]] == case["comm"], (name, opts)
         n += 1
     assert n >= 8
 

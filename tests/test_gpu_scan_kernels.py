@@ -10,7 +10,7 @@ from test_gpu_parity import as_single, gpu, is_weighted, run_single  # noqa: F40
 
 pytestmark = pytest.mark.gpu
 EDGE = np.dtype([("tail", "<i8"), ("weight", "<f8")])
-VARIANTS = [3, 4, 5]
+VARIANTS = [3, 4, 5, 6]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
