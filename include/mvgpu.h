@@ -105,8 +105,8 @@ int mvgpu_get_communities_device(mvgpu_ctx *ctx, const int32_t **d_out);
 /* Options: "trace" (0/1: record moved/chash per iteration, default 0), "max_iters" (safety cap,
  * default 10000), "force_weighted" (0/1: use the fp64 path even for unit weights, default 0),
  * "force_heavy_deg" (test hook: treat vertices with degree > value as high-degree, default 0 = off),
- * "scan_variant" (6 (default): iterations 2-4 and 6 run k_scan_pw, iteration 5 k_scan_pq, and the faster of the two
- * runs from iteration 7 on; 5 = k_scan_pq: persistent warps fed by TMA bulk copies, boundary vertices reduced from a
+ * "scan_variant" (6 (default): iterations 2 and 4 run k_scan_pw, iteration 3 k_scan_pq, and from iteration 5 on
+ * k_scan_pq runs if it beat the geometric mean of its neighbours, else k_scan_pw; 5 = k_scan_pq: persistent warps fed by TMA bulk copies, boundary vertices reduced from a
  * per-warp ring -- unit weights; iteration 1 and weighted graphs run k_scan_pw; 4 = k_scan_pw throughout; 3 =
  * k_scan_ws: one CTA per 128-vertex tile, the default of round 1; identical results), "first_iter" (1 (default):
  * iteration 1 of a simple unit-weight graph uses the singleton-community reduction of k_scan_pw; 0: the general

@@ -838,13 +838,15 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
     CK(cudaEventRecord(e0, s));
     // iteration 1 of a simple graph: every community is a singleton (scan_pipe.cuh, FIRST)
     // Which persistent kernel?  k_scan_pq wins where the gathers hit L1 (RGG: 0.49 vs 0.60 ms per launch) and loses
-    // badly where they do not (its single tail buffer exposes the bulk-copy latency: -p 2 graph, 1.40 vs 0.80 ms), so
-    // scan_variant 6 (default) measures: iterations 2-4 and 6 run k_scan_pw, iteration 5 k_scan_pq, and from iteration 7
-    // on the kernel that was faster than the mean of its two neighbours runs.  Results are identical either way.
+    // badly where they do not (its single tail buffer exposes the bulk-copy latency: -p 2 graph, 1.40 vs 0.80 ms), and
+    // that already shows in iteration 3.  scan_variant 6 (default) therefore measures: iterations 2 and 4 run
+    // k_scan_pw, iteration 3 k_scan_pq, and from iteration 5 on k_scan_pq runs if its launch was faster than the
+    // geometric mean of its two neighbours (scan times fall roughly geometrically there), else k_scan_pw.  Results
+    // are identical either way; every rank decides for itself.
     c->scan_kernel = c->opt_scan_variant == 5 ? 5 : 4;
     if (c->opt_scan_variant == 6) {
-      if (numIters == 5) c->scan_kernel = 5;
-      else if (numIters >= 7) c->scan_kernel = auto_choice;
+      if (numIters == 3) c->scan_kernel = 5;
+      else if (numIters >= 5) c->scan_kernel = auto_choice;
     }
     TRY(launch_scan(c, sp, numIters == 1 && c->simple_sorted && c->opt_first_iter && c->opt_scan_variant >= 4 && !c->f32));
     CK(cudaEventRecord(e1, s));
@@ -901,12 +903,12 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       a2_x = c->unit ? (double)mail->acc.la2_u : mail->acc.la2_d;
       moved = mail->acc.moved; hash = mail->acc.hash;
     }
-    if (c->opt_scan_variant == 6 && numIters == 6) {           // iterations 4..6 have completed (the stream was just synchronised)
-      float t4 = 0, t5 = 0, t6 = 0;
+    if (c->opt_scan_variant == 6 && numIters == 4) {           // iterations 2..4 have completed (the stream was just synchronised)
+      float t2 = 0, t3 = 0, t4 = 0;
+      CK(cudaEventElapsedTime(&t2, c->events[ev_iter0 + 4 * 1], c->events[ev_iter0 + 4 * 1 + 1]));
+      CK(cudaEventElapsedTime(&t3, c->events[ev_iter0 + 4 * 2], c->events[ev_iter0 + 4 * 2 + 1]));
       CK(cudaEventElapsedTime(&t4, c->events[ev_iter0 + 4 * 3], c->events[ev_iter0 + 4 * 3 + 1]));
-      CK(cudaEventElapsedTime(&t5, c->events[ev_iter0 + 4 * 4], c->events[ev_iter0 + 4 * 4 + 1]));
-      CK(cudaEventElapsedTime(&t6, c->events[ev_iter0 + 4 * 5], c->events[ev_iter0 + 4 * 5 + 1]));
-      auto_choice = (t5 < 0.5f * (t4 + t6)) ? 5 : 4;
+      auto_choice = ((double)t3 * t3 < (double)t2 * t4) ? 5 : 4;
       c->tm.scan_kernel_chosen = auto_choice;
     }
     // dspl.hpp:447-448
