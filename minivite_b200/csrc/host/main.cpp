@@ -202,7 +202,12 @@ int main(int argc, char *argv[]) {
 
   // ---- communicator bootstrap (stands in for MPI_Init + createCommunityMPIType, main.cpp:78-102)
   GpuRankContext rc;
-  rc.device = me;
+  {
+    // one GPU per rank; with more ranks than GPUs the ranks wrap around (only the host transport, MVGPU_OPTIONS=
+    // host_transport=1, lets several ranks share a device: NCCL refuses)
+    const int ngpu = mvgpu_device_count();
+    rc.device = ngpu > 0 ? me % ngpu : me;
+  }
   rc.trace = traceIters;
   std::vector<GraphElem> comm;
   if (!dumpPrefix.empty()) rc.comm_out = &comm;

@@ -58,3 +58,19 @@ def test_cli_device_generation(tmp_path, golden):
     assert f"Number of edges: {case['ne']}" in p.stdout
     it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
     assert [(float(a[1]), int(a[2]), a[3]) for a in it] == [(float(g["modularity"]), g["moved"], g["chash"]) for g in case["trace"]]
+
+
+def test_cli_ranks_sharing_one_device(golden):
+    """`-g 2` on a one-GPU box: the ranks (forked processes, like `mpirun -n 2`) wrap around onto device 0 and bootstrap
+    through the host transport.  Host-generated and device-generated (-D) graphs, default RNG and -l: traces equal the
+    reference's own 2-rank runs of `miniVite -n 16384 [-l]` (goldens from the reference's generator)."""
+    import os
+    env = dict(os.environ, MVGPU_OPTIONS="host_transport=1")
+    for args, name in ((["-n", "16384"], "rgg_n16384_p2"), (["-n", "16384", "-D"], "rgg_n16384_p2"),
+                       (["-n", "16384", "-l"], "rgg_n16384_p2_l"), (["-n", "16384", "-l", "-D"], "rgg_n16384_p2_l")):
+        case = golden[name]
+        p = subprocess.run([EXE, "-g", "2", "-T"] + args, capture_output=True, text=True, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert f"Number of edges: {case['ne']}" in p.stdout
+        it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
+        assert [(float(a[1]), int(a[2]), a[3]) for a in it] == [(float(g["modularity"]), g["moved"], g["chash"]) for g in case["trace"]], args
