@@ -793,14 +793,19 @@ __device__ __forceinline__ uint32_t fold_apply_unit(uint32_t dg, unsigned long l
   if (dsize) *csize_i += dsize;
   return dg + (uint32_t)ddeg;
 }
-__global__ void __launch_bounds__(256) k_fold_unit(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, Acc *acc) {
+__global__ void __launch_bounds__(256) k_fold_unit(int lnv, uint32_t *cdeg, int32_t *csize, unsigned long long *upd, Acc *acc,
+                                                   const Acc *prev) {
+  // sum(degree^2) is carried from iteration to iteration (prev->la2_u; record 0 holds the initial sum, written by
+  // k_vertex_init) and only corrected by new^2 - old^2 of the communities that changed -- exact in wrapping 64-bit
+  // arithmetic --, so the pass streams the 8-byte delta array alone and touches cdeg / csize only where a delta is.
   unsigned long long a2u = 0;
   const int n4 = lnv >> 2;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
-    uint4 dg = reinterpret_cast<const uint4 *>(cdeg)[q];
     const ulonglong2 ua = reinterpret_cast<const ulonglong2 *>(upd)[2 * q], ub = reinterpret_cast<const ulonglong2 *>(upd)[2 * q + 1];
     if (ua.x | ua.y | ub.x | ub.y) {
       const int i = 4 * q;
+      uint4 dg = reinterpret_cast<const uint4 *>(cdeg)[q];
+      const uint4 old = dg;
       if (ua.x) dg.x = fold_apply_unit(dg.x, ua.x, csize + i);
       if (ua.y) dg.y = fold_apply_unit(dg.y, ua.y, csize + i + 1);
       if (ub.x) dg.z = fold_apply_unit(dg.z, ub.x, csize + i + 2);
@@ -809,33 +814,40 @@ __global__ void __launch_bounds__(256) k_fold_unit(int lnv, uint32_t *cdeg, int3
       const ulonglong2 z = make_ulonglong2(0ULL, 0ULL);
       if (ua.x | ua.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q] = z;
       if (ub.x | ub.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q + 1] = z;
+      a2u += (unsigned long long)dg.x * dg.x + (unsigned long long)dg.y * dg.y + (unsigned long long)dg.z * dg.z +
+             (unsigned long long)dg.w * dg.w;
+      a2u -= (unsigned long long)old.x * old.x + (unsigned long long)old.y * old.y + (unsigned long long)old.z * old.z +
+             (unsigned long long)old.w * old.w;
     }
-    a2u += (unsigned long long)dg.x * dg.x + (unsigned long long)dg.y * dg.y + (unsigned long long)dg.z * dg.z +
-           (unsigned long long)dg.w * dg.w;
   }
   if (blockIdx.x == 0) {                          // the up to three slots behind the last full group
     const int i = 4 * n4 + (int)threadIdx.x;
     if (i < lnv) {
-      uint32_t dg = cdeg[i];
       const unsigned long long u = upd[i];
-      if (u) { dg = fold_apply_unit(dg, u, csize + i); cdeg[i] = dg; upd[i] = 0; }
-      a2u += (unsigned long long)dg * dg;
+      if (u) {
+        const uint32_t old = cdeg[i];
+        const uint32_t dg = fold_apply_unit(old, u, csize + i);
+        cdeg[i] = dg; upd[i] = 0;
+        a2u += (unsigned long long)dg * dg - (unsigned long long)old * old;
+      }
     }
+    if (threadIdx.x == 0) a2u += prev->la2_u;     // complete: the previous iteration's fold has finished
   }
   __shared__ unsigned long long su[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned long long s = warp_sum(a2u);
   if (lane == 0) su[wid] = s;
   __syncthreads();
-  if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < 8; w++) t += su[w]; atomicAdd(&acc->la2_u, t); }
+  if (threadIdx.x == 0) { unsigned long long t = 0; for (int w = 0; w < 8; w++) t += su[w]; if (t) atomicAdd(&acc->la2_u, t); }
 }
 template <bool UNIT>
 __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, const uint32_t *rowptr, const int32_t *tails,
                                                      const double *weights, int32_t *cur, uint32_t *cdeg, int32_t *csize,
                                                      unsigned long long *upd, CommW *cinfo_w, long long *usize, double *udeg,
                                                      double *vdeg, int32_t *self_i, double *self_d, double *total_weight,
-                                                     unsigned int *has_self, int nlow, unsigned int *unordered) {
+                                                     unsigned int *has_self, int nlow, unsigned int *unordered, Acc *acc0) {
   double tw_sum = 0.0;
+  unsigned long long sq_sum = 0;                 // unit path: initial sum(degree^2), the fold kernel's starting point
   unsigned int any_self = 0;
   bool bad = false;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < lnv; v += gridDim.x * blockDim.x) {
@@ -859,6 +871,7 @@ __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, co
       csize[v] = 1;
       upd[v] = 0;
       tw_sum += (double)(e1 - e0);
+      sq_sum += (unsigned long long)(e1 - e0) * (e1 - e0);
     } else {
       double tw = 0.0, sl = 0.0;
       for (uint32_t e = e0; e < e1; e++) {           // edge order, like dspl.hpp:97-100
@@ -876,9 +889,11 @@ __global__ void __launch_bounds__(256) k_vertex_init(int lnv, long long base, co
     }
   }
   tw_sum = warp_sum(tw_sum);
+  if (UNIT) sq_sum = warp_sum(sq_sum);
   any_self = __any_sync(0xffffffffu, any_self);
   if (bad) *unordered = 1;
   if ((threadIdx.x & 31) == 0) {
+    if (UNIT && sq_sum) atomicAdd(&acc0->la2_u, sq_sum);
     if (tw_sum != 0.0) atomicAdd(total_weight, tw_sum);
     if (any_self) atomicOr(has_self, 1u);
   }

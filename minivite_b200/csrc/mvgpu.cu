@@ -718,11 +718,11 @@ int setup_run(mvgpu_ctx *c) {
     k_vertex_init<true><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, nullptr, c->comm_a.p,
                                                               c->cdeg.p, c->csize.p, c->upd.p, nullptr, nullptr, nullptr, nullptr,
                                                               c->self_i.p, nullptr, &d_sc->total_weight, &d_sc->has_self,
-                                                              (int)c->roff[c->rank], c->reordered ? nullptr : &d_sc->unordered);
+                                                              (int)c->roff[c->rank], c->reordered ? nullptr : &d_sc->unordered, c->acc.p);
   else
     k_vertex_init<false><<<grid_for(lnv, 256, nsm), 256, 0, s>>>((int)lnv, c->base, c->a_rowptr, c->a_tails, c->a_weights, c->comm_a.p,
                                                                nullptr, nullptr, nullptr, c->cinfo_w.p, c->usize.p, c->udeg.p, c->vdeg.p,
-                                                               nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self, 0, nullptr);
+                                                               nullptr, c->self_d.p, &d_sc->total_weight, &d_sc->has_self, 0, nullptr, nullptr);
   c->tm.kernel_launches++;
   // ghosts start in their own (internal) singleton community, which only the owner knows after renumbering:
   // fetch it with the same all-to-all-v the iterations use
@@ -867,7 +867,7 @@ int run_louvain(mvgpu_ctx *c, double lower, double thresh, int *iters_out, doubl
       }
     }
     CK(cudaEventRecord(e2, s));
-    if (c->unit) k_fold_unit<<<grid_for((c->lnv >> 2) + 1, 256, c->num_sms, 8), 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, acc);
+    if (c->unit) k_fold_unit<<<grid_for((c->lnv >> 2) + 1, 256, c->num_sms, 8), 256, 0, s>>>((int)c->lnv, c->cdeg.p, c->csize.p, c->upd.p, acc, acc - 1);
     else k_fold_w<<<fold_grid, 256, 0, s>>>((int)c->lnv, c->cinfo_w.p, c->usize.p, c->udeg.p, acc);
     c->tm.kernel_launches++;
     CK(cudaEventRecord(e3, s));
