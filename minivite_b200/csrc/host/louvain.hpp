@@ -79,9 +79,9 @@ inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph
   ssizes.clear(); rsizes.clear(); svdata.clear(); rvdata.clear();
   mvgpu_ctx *ctx = nullptr;
   if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
+  mv_apply_env_options(ctx);                       // before the communicator: host_transport decides how it is built
   if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
   if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
-  mv_apply_env_options(ctx);
   if (mvgpu_upload_shard(ctx, dg.get_nv(), dg.parts().data(), dg.get_lnv(), dg.get_lne(), dg.edge_indices_.data(),
                          dg.edge_list_.data()))
     mv_abort("mvgpu_upload_shard");
@@ -113,9 +113,9 @@ inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, 
                                                 const std::function<void()> &before_louvain) {
   mvgpu_ctx *ctx = nullptr;
   if (mvgpu_create(&ctx, rc.device, me, nprocs)) mv_abort("mvgpu_create");
+  mv_apply_env_options(ctx);                       // before the communicator: host_transport decides how it is built
   if (nprocs > 1 && mvgpu_comm_init(ctx, rc.unique_id)) mv_abort("mvgpu_comm_init");
   if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
-  mv_apply_env_options(ctx);
   const auto t0 = std::chrono::steady_clock::now();
   int64_t lne64 = 0;
   if (mvgpu_generate_rgg_shard_ex(ctx, nv, unitEdgeWeight ? 1 : 0, lcg ? 1 : 0, &lne64)) mv_abort("mvgpu_generate_rgg_shard");

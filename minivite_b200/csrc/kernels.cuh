@@ -800,25 +800,41 @@ __global__ void __launch_bounds__(256) k_fold_unit(int lnv, uint32_t *cdeg, int3
   // arithmetic --, so the pass streams the 8-byte delta array alone and touches cdeg / csize only where a delta is.
   unsigned long long a2u = 0;
   const int n4 = lnv >> 2;
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
-    const ulonglong2 ua = reinterpret_cast<const ulonglong2 *>(upd)[2 * q], ub = reinterpret_cast<const ulonglong2 *>(upd)[2 * q + 1];
-    if (ua.x | ua.y | ub.x | ub.y) {
-      const int i = 4 * q;
-      uint4 dg = reinterpret_cast<const uint4 *>(cdeg)[q];
-      const uint4 old = dg;
-      if (ua.x) dg.x = fold_apply_unit(dg.x, ua.x, csize + i);
-      if (ua.y) dg.y = fold_apply_unit(dg.y, ua.y, csize + i + 1);
-      if (ub.x) dg.z = fold_apply_unit(dg.z, ub.x, csize + i + 2);
-      if (ub.y) dg.w = fold_apply_unit(dg.w, ub.y, csize + i + 3);
-      reinterpret_cast<uint4 *>(cdeg)[q] = dg;
-      const ulonglong2 z = make_ulonglong2(0ULL, 0ULL);
-      if (ua.x | ua.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q] = z;
-      if (ub.x | ub.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q + 1] = z;
-      a2u += (unsigned long long)dg.x * dg.x + (unsigned long long)dg.y * dg.y + (unsigned long long)dg.z * dg.z +
-             (unsigned long long)dg.w * dg.w;
-      a2u -= (unsigned long long)old.x * old.x + (unsigned long long)old.y * old.y + (unsigned long long)old.z * old.z +
-             (unsigned long long)old.w * old.w;
+  auto apply4 = [&](int q, const ulonglong2 ua, const ulonglong2 ub) {
+    const int i = 4 * q;
+    uint4 dg = reinterpret_cast<const uint4 *>(cdeg)[q];
+    const uint4 old = dg;
+    if (ua.x) dg.x = fold_apply_unit(dg.x, ua.x, csize + i);
+    if (ua.y) dg.y = fold_apply_unit(dg.y, ua.y, csize + i + 1);
+    if (ub.x) dg.z = fold_apply_unit(dg.z, ub.x, csize + i + 2);
+    if (ub.y) dg.w = fold_apply_unit(dg.w, ub.y, csize + i + 3);
+    reinterpret_cast<uint4 *>(cdeg)[q] = dg;
+    const ulonglong2 z = make_ulonglong2(0ULL, 0ULL);
+    if (ua.x | ua.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q] = z;
+    if (ub.x | ub.y) reinterpret_cast<ulonglong2 *>(upd)[2 * q + 1] = z;
+    a2u += (unsigned long long)dg.x * dg.x + (unsigned long long)dg.y * dg.y + (unsigned long long)dg.z * dg.z +
+           (unsigned long long)dg.w * dg.w;
+    a2u -= (unsigned long long)old.x * old.x + (unsigned long long)old.y * old.y + (unsigned long long)old.z * old.z +
+           (unsigned long long)old.w * old.w;
+  };
+  // four groups of four slots per thread and step: eight 16-byte loads in flight before the first is looked at
+  constexpr int kU = 4;
+  const int stride = gridDim.x * blockDim.x;
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; q + (kU - 1) * stride < n4; q += kU * stride) {
+    ulonglong2 ua[kU], ub[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      ua[u] = reinterpret_cast<const ulonglong2 *>(upd)[2 * (q + u * stride)];
+      ub[u] = reinterpret_cast<const ulonglong2 *>(upd)[2 * (q + u * stride) + 1];
     }
+#pragma unroll
+    for (int u = 0; u < kU; u++)
+      if (ua[u].x | ua[u].y | ub[u].x | ub[u].y) apply4(q + u * stride, ua[u], ub[u]);
+  }
+  for (; q < n4; q += stride) {
+    const ulonglong2 ua = reinterpret_cast<const ulonglong2 *>(upd)[2 * q], ub = reinterpret_cast<const ulonglong2 *>(upd)[2 * q + 1];
+    if (ua.x | ua.y | ub.x | ub.y) apply4(q, ua, ub);
   }
   if (blockIdx.x == 0) {                          // the up to three slots behind the last full group
     const int i = 4 * n4 + (int)threadIdx.x;

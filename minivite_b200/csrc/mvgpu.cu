@@ -1460,7 +1460,10 @@ int mvgpu_set_option(mvgpu_ctx *c, const char *name, int64_t value) {
   else if (n == "host_threads") c->opt_host_threads = (int)value;
   else if (n == "first_iter") c->opt_first_iter = value != 0;
   else if (n == "upload_chunk") { if (value < 256 || (value & 3)) return fail("upload_chunk must be a multiple of 4, >= 256"); c->opt_upload_chunk = value; }
-  else if (n == "host_transport") { if (c->comm || c->hc.is_open()) return fail("host_transport must be set before mvgpu_comm_init"); c->opt_host_transport = value != 0; }
+  else if (n == "host_transport") {
+    if ((c->comm || c->hc.is_open()) && c->opt_host_transport != (value != 0)) return fail("host_transport must be set before mvgpu_comm_init");
+    c->opt_host_transport = value != 0;
+  }
   else if (n == "region_size") { if (value < 32) return fail("region_size < 32"); c->opt_region = (int)value; }
   else return fail("unknown option " + n);
   return 0;
