@@ -655,7 +655,8 @@ __global__ void __launch_bounds__(256) k_edge_stats(const Edge16 *edges, long lo
 // the pass also gathers the statistics of k_edge_stats (single-rank runs need no separate statistics pass).
 __global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long long lne, long long base, long long bound,
                                                        long long nv_global, int32_t *tails, double *weights,
-                                                       long long *remote_list, unsigned long long *remote_cursor, EdgeStats *st) {
+                                                       long long *remote_list, uint32_t *remote_pos,
+                                                       unsigned long long *remote_cursor, EdgeStats *st) {
   unsigned long long nrem = 0;
   unsigned int nonunit = 0, bad = 0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
@@ -672,6 +673,7 @@ __global__ void __launch_bounds__(256) k_convert_edges(const Edge16 *edges, long
     if (!local && remote_list) {
       const unsigned long long pos = atomicAdd(remote_cursor, 1ULL);
       remote_list[pos] = t;
+      remote_pos[pos] = (uint32_t)e;              // where the ghost slot has to go (k_remap_ghost_tails)
     }
   }
   if (st) {
@@ -734,7 +736,8 @@ __global__ void __launch_bounds__(256) k_narrow_records(const Edge16 *rec, long 
 
 // same conversion for the compact upload format (int32 global tails, unit weights; see mvgpu_upload_shard)
 __global__ void __launch_bounds__(256) k_convert_tails32(const int32_t *gtails, long long lne, long long base, long long bound,
-                                                         int32_t *tails, long long *remote_list, unsigned long long *remote_cursor) {
+                                                         int32_t *tails, long long *remote_list, uint32_t *remote_pos,
+                                                         unsigned long long *remote_cursor) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
     const long long t = __ldcs(gtails + e);
     const bool local = (t >= base && t < bound);
@@ -742,19 +745,20 @@ __global__ void __launch_bounds__(256) k_convert_tails32(const int32_t *gtails, 
     if (!local && remote_list) {
       const unsigned long long pos = atomicAdd(remote_cursor, 1ULL);
       remote_list[pos] = t;
+      remote_pos[pos] = (uint32_t)e;
     }
   }
 }
 
 // ghosts: slot = lnv + rank of the tail in the sorted unique ghost list
-__global__ void __launch_bounds__(256) k_remap_ghost_tails(const Edge16 *edges, const int32_t *gtails, long long lne, int32_t *tails,
-                                                           const long long *ghost_gid, int nghost, int lnv) {
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < lne; e += (long long)gridDim.x * blockDim.x) {
-    if (tails[e] >= 0) continue;
-    const long long t = edges ? edges[e].tail : (long long)gtails[e];
+__global__ void __launch_bounds__(256) k_remap_ghost_tails(const long long *remote_list, const uint32_t *remote_pos, long long nremote,
+                                                           int32_t *tails, const long long *ghost_gid, int nghost, int lnv) {
+  // one thread per NON-OWNED edge (their positions were recorded by the conversion pass), not one per edge of the shard
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nremote; k += (long long)gridDim.x * blockDim.x) {
+    const long long t = remote_list[k];
     int lo = 0, hi = nghost;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (ghost_gid[mid] < t) lo = mid + 1; else hi = mid; }
-    tails[e] = lnv + lo;
+    tails[remote_pos[k]] = lnv + lo;
   }
 }
 

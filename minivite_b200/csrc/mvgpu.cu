@@ -153,6 +153,7 @@ struct mvgpu_ctx {
   DevBuf<long long> sorted_tmp;
   // ghosts
   DevBuf<long long> remote_list, ghost_gid, send_gid;
+  DevBuf<uint32_t> remote_pos;
   DevBuf<int32_t> send_lid, send_buf;
   long long nghost = 0, nsend = 0;
   std::vector<long long> rcount, scount, roff, soff;   // per peer
@@ -472,7 +473,7 @@ int setup_run(mvgpu_ctx *c) {
   if (fused_stats) {
     TRY(c->tails.ensure(lne + 4));
     k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, c->tails.p,
-                                                              nullptr, nullptr, nullptr, &d_sc->st);
+                                                              nullptr, nullptr, nullptr, nullptr, &d_sc->st);
     c->tm.kernel_launches++;
   } else if (!compact_in) {
     k_edge_stats<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, &d_sc->st);
@@ -522,7 +523,7 @@ int setup_run(mvgpu_ctx *c) {
 
   // pass 2: tails -> slots, weights split off, remote tails listed
   const long long nremote = (long long)h.st.nremote;
-  if (nremote) TRY(c->remote_list.ensure(nremote));
+  if (nremote) { TRY(c->remote_list.ensure(nremote)); TRY(c->remote_pos.ensure(nremote)); }
   const uint32_t *src_rowptr = c->rowptr.p;
   const int32_t *src_tails = nullptr;
   const double *src_weights = nullptr;
@@ -547,11 +548,11 @@ int setup_run(mvgpu_ctx *c) {
     if (!c->unit) TRY(c->weights.ensure(lne + 4));
     if (compact_in)
       k_convert_tails32<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_tails32, lne, c->base, c->bound, c->tails.p,
-                                                                  nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor);
+                                                                  nremote ? c->remote_list.p : nullptr, c->remote_pos.p, &d_sc->remote_cursor);
     else
       k_convert_edges<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->d_edges, lne, c->base, c->bound, c->nv_global, c->tails.p,
                                                                 c->unit ? nullptr : c->weights.p,
-                                                                nremote ? c->remote_list.p : nullptr, &d_sc->remote_cursor, nullptr);
+                                                                nremote ? c->remote_list.p : nullptr, c->remote_pos.p, &d_sc->remote_cursor, nullptr);
     c->tm.kernel_launches++;
     if (compact_in && !c->unit) {                   // a peer's shard is weighted (or 2m >= 2^31): this one's weights are all 1.0
       k_fill_ones<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(c->weights.p, lne);
@@ -586,7 +587,7 @@ int setup_run(mvgpu_ctx *c) {
       CK(cudaStreamSynchronize(s));
       c->nghost = nu;
       if (lnv + c->nghost >= (1LL << 31)) return fail("lnv + nghost >= 2^31");
-      k_remap_ghost_tails<<<grid_for(lne, 256, nsm, 16), 256, 0, s>>>(compact_in ? nullptr : c->d_edges, c->d_tails32, lne, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
+      k_remap_ghost_tails<<<grid_for(nremote, 256, nsm, 16), 256, 0, s>>>(c->remote_list.p, c->remote_pos.p, nremote, c->tails.p, c->ghost_gid.p, (int)c->nghost, (int)lnv);
       c->tm.kernel_launches++;
       // per-owner counts of my ghosts (the list is sorted, owners are contiguous ranges)
       std::vector<long long> hg(c->nghost);
@@ -1060,7 +1061,7 @@ int mvgpu_destroy(mvgpu_ctx *c) {
   c->in_rowptr.release(); c->in_edges.release(); c->rowptr.release(); c->tails.release(); c->weights.release();
   c->self_i.release(); c->self_d.release(); c->vdeg.release(); c->comm_a.release(); c->comm_b.release();
   c->cdeg.release(); c->csize.release(); c->upd.release(); c->cinfo_w.release(); c->usize.release(); c->udeg.release(); c->acc.release();
-  c->scratch.release(); c->cub_tmp.release(); c->coll_tmp.release(); c->sorted_tmp.release(); c->remote_list.release(); c->ghost_gid.release(); c->send_gid.release();
+  c->scratch.release(); c->cub_tmp.release(); c->coll_tmp.release(); c->sorted_tmp.release(); c->remote_list.release(); c->remote_pos.release(); c->ghost_gid.release(); c->send_gid.release();
   c->bfs_key.release(); c->sortkey.release(); c->sortkey2.release(); c->deg_new.release(); c->rowptr2.release();
   c->ids.release(); c->perm.release(); c->inv.release(); c->lab.release(); c->tails2.release(); c->final_orig.release();
   c->weights2.release(); c->level_flags.release();
