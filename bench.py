@@ -436,7 +436,7 @@ def main():
     #                                            + 4 cur + 8 cinfo + 4 tgt write + 8 (packed delta atomics, 2 x 57% ~ 1)
     roof = {"bound": "hbm", "achieved": b_alg / t_scan_iter / 1e9, "peak": peak, "unit": "GB/s",
             "frac": b_alg / t_scan_iter / 1e9 / peak, "traffic": None,
-            "kernel": "neighbour scan (k_scan_pw / k_scan_ws)", "algorithmic_bytes_per_launch": b_alg,
+            "kernel": "neighbour scan (k_scan_pq / k_scan_pw, chosen at run time; scan_pipe.cuh, scan_queue.cuh)", "algorithmic_bytes_per_launch": b_alg,
             "definition": "achieved = SURVEY 8(d) canonical bytes (24*ne + 56*nv, the reference's 64-bit element sizes) / "
                           "avg launch time; the kernel moves fewer bytes than that (32-bit ids, implicit unit weights, "
                           "cached gathers), so see frac_own_layout and frac_dram_traffic for what the hardware did",

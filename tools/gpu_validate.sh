@@ -4,6 +4,7 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 O=gpurun_out/${1:-val}
+python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.log 2>&1; tail -n 2 ${O}_smoke.log
 timeout 2400 python -m pytest tests -x -q -m gpu -rA > ${O}_pytest_all.log 2>&1
 grep -E "passed|failed|error" ${O}_pytest_all.log | tail -3
 MVGPU_SCAN_TIMES=1 MVGPU_REPEAT=3 timeout 120 bin/miniVite_b200 -n 16777216 -D 2>&1 | grep -E "TIMINGS|RESULT|SCAN_MS|rror" | tee ${O}_cli.log
