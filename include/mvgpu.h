@@ -82,13 +82,18 @@ int mvgpu_upload_shard(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, 
 int mvgpu_attach_shard_device(mvgpu_ctx *ctx, int64_t nv_global, const int64_t *parts, int64_t lnv, int64_t lne,
                               const int64_t *d_edge_indices, const void *d_edge_list);
 
-/* Device-side GenerateRGG (graph.hpp:584-1213, no -p): builds this rank's strip of the graph
+/* Device-side GenerateRGG (graph.hpp:584-1213): builds this rank's strip of the graph
  * `miniVite -n nv_global` creates on nranks ranks directly in HBM, bit-identical to the reference generator, and
  * attaches it as the context's shard.  unit_weight = 0 gives Euclidean edge weights (-w).  *lne_out: local edges. */
 int mvgpu_generate_rgg_shard(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int64_t *lne_out);
-/* Same with the choice of random numbers: lcg = 1 draws the coordinates from the reference's LCG class like
- * `miniVite -n nv_global -l` (utils.hpp:118-303, graph.hpp:703-729), lcg = 0 is the default engine. */
-int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int lcg, int64_t *lne_out);
+/* Same with the remaining generator switches: lcg = 1 draws the coordinates from the reference's LCG class like
+ * `miniVite -n nv_global -l` (utils.hpp:118-303, graph.hpp:703-729), lcg = 0 is the default engine;
+ * random_edge_percent > 0 adds that percentage of random long edges like `-p` (graph.hpp:939-1122; the reference
+ * seeds them from time and pid, graph.hpp:990, this library from a fixed seed -- the same one its host generator
+ * uses, so both build the same graph).  With nranks > 1 and random_edge_percent > 0 the call is collective and needs
+ * mvgpu_comm_init first (one count is summed over the ranks, graph.hpp:941-943). */
+int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *ctx, int64_t nv_global, int unit_weight, int lcg, double random_edge_percent,
+                                int64_t *lne_out);
 /* Copy the shard's reference-format arrays (lnv+1 offsets, lne 16-byte records) back to the host. */
 int mvgpu_download_shard(mvgpu_ctx *ctx, int64_t *edge_indices, void *edge_list);
 

@@ -108,7 +108,7 @@ inline GraphWeight distLouvainMethod(const int me, const int nprocs, const Graph
 // the reference's generator of graph.hpp:584-1213 bit for bit) and the Louvain phase consumes it in place.
 // `gen_seconds` receives the generation time, `lne` the local edge count.
 inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, const GraphElem nv, const bool unitEdgeWeight,
-                                                const bool lcg, const GraphWeight lower, const GraphWeight thresh, int &iters,
+                                                const bool lcg, const GraphWeight randomEdgePercent, const GraphWeight lower, const GraphWeight thresh, int &iters,
                                                 GpuRankContext &rc, GraphElem &lne, double &gen_seconds,
                                                 const std::function<void()> &before_louvain) {
   mvgpu_ctx *ctx = nullptr;
@@ -118,7 +118,7 @@ inline GraphWeight distLouvainMethodOnDeviceRGG(const int me, const int nprocs, 
   if (rc.trace) mvgpu_set_option(ctx, "trace", 1);
   const auto t0 = std::chrono::steady_clock::now();
   int64_t lne64 = 0;
-  if (mvgpu_generate_rgg_shard_ex(ctx, nv, unitEdgeWeight ? 1 : 0, lcg ? 1 : 0, &lne64)) mv_abort("mvgpu_generate_rgg_shard");
+  if (mvgpu_generate_rgg_shard_ex(ctx, nv, unitEdgeWeight ? 1 : 0, lcg ? 1 : 0, randomEdgePercent, &lne64)) mv_abort("mvgpu_generate_rgg_shard");
   gen_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   lne = lne64;
   before_louvain();

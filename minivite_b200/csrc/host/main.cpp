@@ -7,7 +7,7 @@
 //   -t <thr>   convergence threshold      -n <nv> generate an RGG          -w  Euclidean edge weights
 //   -l         LCG random numbers         -p <pct> extra random edges      -s  print the graph
 // additions: -g <gpus> (default 1)   -o <prefix> dump final communities per rank   -T per-iteration trace on stderr
-//            -D generate the RGG on the GPU (same graph; with -n, also -w and -l; without -p/-s)
+//            -D generate the RGG on the GPU (same graph; with -n, also -w, -l and -p; without -s)
 #include <getopt.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -115,8 +115,8 @@ static void parseCommandLine(const int argc, char *const argv[]) {
     std::cerr << "Invalid random edge percentage for generated graph!" << std::endl; exit(99);
   }
   if (nprocs < 1 || nprocs > 16) { std::cerr << "Invalid number of GPUs (-g)." << std::endl; exit(99); }
-  if (deviceGenerate && (!generateGraph || randomEdgePercent > 0.0 || showGraph)) {
-    std::cerr << "-D (generate the RGG on the GPU) needs -n and excludes -p and -s." << std::endl; exit(99);
+  if (deviceGenerate && (!generateGraph || showGraph)) {
+    std::cerr << "-D (generate the RGG on the GPU) needs -n and excludes -s." << std::endl; exit(99);
   }
 }
 
@@ -230,7 +230,7 @@ int main(int argc, char *argv[]) {
   if (deviceGenerate) {
     GraphElem lne = 0;
     double gen_s = 0.0;
-    currMod = distLouvainMethodOnDeviceRGG(me, nprocs, nvRGG, isUnitEdgeWeight, randomNumberLCG, currMod, threshold, iters, rc, lne, gen_s, [&]() {
+    currMod = distLouvainMethodOnDeviceRGG(me, nprocs, nvRGG, isUnitEdgeWeight, randomNumberLCG, randomEdgePercent, currMod, threshold, iters, rc, lne, gen_s, [&]() {
       ne_rep = reduce_sum_ll(lne);                 // between generation and the Louvain phase: the reference's report + timer start
       print_stats((long)lne, nvRGG, ne_rep);
       const double tdt = reduce_sum(gen_s);

@@ -995,6 +995,84 @@ __global__ void k_widen(const int32_t *in, long long n, long long *out) {
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// `-p`: random long edges on top of the generated strip (graph.hpp:939-1122; host/rgg.hpp add_random_edges is the
+// restatement this follows, including its fixed seed).  Every rank replays all p draw streams (they are cheap and
+// sequential) and keeps the records that touch its strip.
+static int add_random_edges(mvgpu_ctx *c, const RggParams &P, int64_t nv, int unit, double pct, const double *X3, const double *Y3,
+                            long long *lne_io) {
+  const int p = c->nranks, nsm = c->num_sms;
+  cudaStream_t s = c->stream;
+  if (nv >= 2147483645LL) return fail("random edges: nv too large for the device generator");
+  long long tot = *lne_io / 2;
+  TRY(coll_allreduce_i64(c, &tot, 1, false));
+  const long long nrande = ((long long)(pct * (double)tot)) / 100;
+  if (nrande <= 0) return 0;
+  if (nrande >= (1LL << 31)) return fail("random edges: too many draws for the device generator");
+  std::vector<long long> soff(p + 1, 0);
+  for (int r = 0; r < p; r++) {
+    long long pn = 0;
+    if (nrande < p) { if (r == p - 1) pn = nrande; }
+    else { pn = nrande / p; if (r == p - 1) pn += nrande % p; }
+    soff[r + 1] = soff[r] + pn;
+  }
+  RandeParams R;
+  R.n = P.n; R.nv = nv; R.p = p; R.me = c->rank; R.seed = 20180912u;       // host/rgg.hpp kRandomEdgeSeed
+  DevBuf<long long> dsoff, nrow;
+  DevBuf<int> di, dgj;
+  DevBuf<unsigned long long> key, skey, xkey, sxkey;
+  DevBuf<unsigned int> qidx, sq, emit, epos, xidx, sxidx, add, xstart;
+  DevBuf<double> xw;
+  TRY(dsoff.ensure(p + 1)); TRY(di.ensure(nrande)); TRY(dgj.ensure(nrande));
+  TRY(key.ensure(nrande)); TRY(skey.ensure(nrande)); TRY(qidx.ensure(nrande)); TRY(sq.ensure(nrande));
+  TRY(emit.ensure(nrande + 1)); TRY(epos.ensure(nrande + 1));
+  CK(cudaMemcpyAsync(dsoff.p, soff.data(), sizeof(long long) * (p + 1), cudaMemcpyHostToDevice, s));
+  k_rande_draws<<<p, 32, 0, s>>>(R, dsoff.p, di.p, dgj.p);
+  k_rande_keys<<<grid_for(nrande, 256, nsm), 256, 0, s>>>(R, dsoff.p, di.p, dgj.p, nrande, c->gen_rowptr.p, c->gen_edges.p, key.p, qidx.p);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, skey.p, qidx.p, sq.p, (int)nrande, 0, 64, s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, key.p, skey.p, qidx.p, sq.p, (int)nrande, 0, 64, s));
+  CK(cudaMemsetAsync(emit.p + nrande, 0, sizeof(unsigned int), s));
+  k_rande_first<<<grid_for(nrande, 256, nsm), 256, 0, s>>>(skey.p, sq.p, nrande, R, dsoff.p, dgj.p, emit.p);
+  tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, emit.p, epos.p, (int)(nrande + 1), s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, emit.p, epos.p, (int)(nrande + 1), s));
+  unsigned int nextra = 0;
+  CK(cudaMemcpyAsync(&nextra, epos.p + nrande, sizeof nextra, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (!nextra) return 0;
+  TRY(xkey.ensure(nextra)); TRY(sxkey.ensure(nextra)); TRY(xidx.ensure(nextra)); TRY(sxidx.ensure(nextra)); TRY(xw.ensure(nextra));
+  TRY(add.ensure(P.n + 1)); TRY(xstart.ensure(P.n + 1)); TRY(nrow.ensure(P.n + 1));
+  CK(cudaMemsetAsync(add.p, 0, sizeof(unsigned int) * (P.n + 1), s));
+  k_rande_emit<<<grid_for(nrande, 256, nsm), 256, 0, s>>>(R, P, dsoff.p, di.p, dgj.p, nrande, emit.p, epos.p, unit, X3, Y3, xkey.p, xw.p,
+                                                        xidx.p, add.p);
+  tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, xkey.p, sxkey.p, xidx.p, sxidx.p, (int)nextra, 0, 62, s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, xkey.p, sxkey.p, xidx.p, sxidx.p, (int)nextra, 0, 62, s));
+  tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, add.p, xstart.p, (int)(P.n + 1), s);
+  TRY(c->cub_tmp.ensure(tb));
+  tb = c->cub_tmp.cap;
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tb, add.p, xstart.p, (int)(P.n + 1), s));
+  k_rande_rowptr<<<grid_for(P.n + 1, 256, nsm), 256, 0, s>>>(c->gen_rowptr.p, xstart.p, P.n, nrow.p);
+  const long long lne2 = *lne_io + (long long)nextra;
+  DevBuf<Edge16> merged;
+  TRY(merged.ensure(lne2));
+  k_rande_merge<<<grid_for(P.n, 256, nsm, 16), 256, 0, s>>>(c->gen_rowptr.p, c->gen_edges.p, xstart.p, sxkey.p, sxidx.p, xw.p, P.n, nrow.p,
+                                                          merged.p);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  std::swap(c->gen_edges.p, merged.p); std::swap(c->gen_edges.cap, merged.cap); c->gen_edges.gen++;
+  std::swap(c->gen_rowptr.p, nrow.p); std::swap(c->gen_rowptr.cap, nrow.cap); c->gen_rowptr.gen++;
+  *lne_io = lne2;
+  return 0;
+}
+
 extern "C" {
 
 const char *mvgpu_last_error(void) { return g_err.c_str(); }
@@ -1272,15 +1350,18 @@ int mvgpu_attach_shard_device(mvgpu_ctx *c, int64_t nv_global, const int64_t *pa
 
 // ---- section 8(f) rank 1: the reference's GenerateRGG on the device (rgg_gpu.cuh) ---------------------------------
 int mvgpu_generate_rgg_shard(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int64_t *lne_out) {
-  return mvgpu_generate_rgg_shard_ex(c, nv_global, unit_weight, 0, lne_out);
+  return mvgpu_generate_rgg_shard_ex(c, nv_global, unit_weight, 0, 0.0, lne_out);
 }
 
-int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int lcg, int64_t *lne_out) {
+int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *c, int64_t nv_global, int unit_weight, int lcg, double random_edge_percent, int64_t *lne_out) {
   if (!c) return fail("null ctx");
   CK(cudaSetDevice(c->device));
   const int p = c->nranks, r = c->rank;
   if (nv_global < 1 || nv_global % p != 0) return fail("[ERROR] Number of vertices must be perfectly divisible by number of processes.");
   if (p & (p - 1)) return fail("[ERROR] Number of processes must be a power of 2.");
+  if (!(random_edge_percent >= 0.0)) return fail("random_edge_percent must be >= 0");
+  if (random_edge_percent > 0.0 && p > 1 && !c->comm && !c->hc.is_open())
+    return fail("random edges (-p) on several ranks need the communicator: call mvgpu_comm_init first");
   RggParams P;
   memset(&P, 0, sizeof P);
   P.n = nv_global / p; P.rank = r; P.nranks = p;
@@ -1368,7 +1449,9 @@ int mvgpu_generate_rgg_shard_ex(mvgpu_ctx *c, int64_t nv_global, int unit_weight
   k_rgg_neighbours<true><<<grid_for(P.n, 128, nsm, 16), 128, 0, s>>>(P, X.p, UY.p, cstart.p, cx.p, cy.p, cgid.p, unit_weight, c->gen_rowptr.p, c->gen_edges.p);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
-  X.release(); UY.release(); cx.release(); cy.release(); cgid.release(); deg.release(); cnt.release(); cstart.release();
+  cx.release(); cy.release(); cgid.release(); deg.release(); cnt.release(); cstart.release();
+  if (random_edge_percent > 0.0) TRY(add_random_edges(c, P, nv_global, unit_weight, random_edge_percent, X.p, UY.p, &lne));
+  X.release(); UY.release();
   std::vector<int64_t> parts(p + 1);
   for (int q = 0; q <= p; q++) parts[q] = (nv_global * q) / p;
   TRY(set_graph(c, nv_global, parts.data(), P.n, lne));

@@ -163,4 +163,160 @@ __global__ void __launch_bounds__(128) k_rgg_neighbours(RggParams p, const doubl
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Random long edges (`-p`, GenerateRGG graph.hpp:939-1122 as host/rgg.hpp add_random_edges restates it with a fixed
+// seed). Stream s (= generating rank s) draws pnrande(s) pairs (i, g_j) from minstd_rand0(seed + s); a pair becomes an
+// edge unless i == j, i -> g_j is an RGG edge of strip s, or stream s added the same pair before. The draws are
+// sequential per stream (one thread each, p streams); everything after them is data parallel.
+// ---------------------------------------------------------------------------------------------------------------
+struct RandeParams {
+  long long n, nv;           // vertices per strip, in total
+  int p, me;
+  unsigned int seed;         // stream s is seeded with seed + s
+};
+
+// libstdc++ uniform_int_distribution over a generator whose range (2147483646 values) is not a power of two:
+// scale down with rejection (bits/uniform_int_dist.h, the "downscaling" branch)
+__device__ __forceinline__ unsigned long long minstd_below(unsigned long long &x, unsigned long long scaling, unsigned long long past) {
+  unsigned long long ret;
+  do {
+    x = mulmod31(x, 16807ULL);
+    ret = x - 1ULL;
+  } while (ret >= past);
+  return ret / scaling;
+}
+
+__global__ void k_rande_draws(RandeParams rp, const long long *soff, int *di, int *dgj) {
+  if (threadIdx.x) return;
+  const int s = blockIdx.x;
+  unsigned long long x = (unsigned long long)(rp.seed + (unsigned int)s) % 2147483647ULL;
+  if (x == 0) x = 1;
+  const unsigned long long sc_i = 2147483645ULL / (unsigned long long)rp.n, past_i = (unsigned long long)rp.n * sc_i;
+  const unsigned long long sc_j = 2147483645ULL / (unsigned long long)rp.nv, past_j = (unsigned long long)rp.nv * sc_j;
+  for (long long q = soff[s]; q < soff[s + 1]; q++) {
+    di[q] = (int)minstd_below(x, sc_i, past_i);
+    dgj[q] = (int)minstd_below(x, sc_j, past_j);
+  }
+}
+
+__device__ __forceinline__ int rande_stream_of(const long long *soff, int p, long long q) {
+  int s = 0;
+  while (s + 1 < p && q >= soff[s + 1]) s++;
+  return s;
+}
+
+// key[q] = (g_i, g_j) packed for the draws that touch this strip and are not RGG edges, ~0 for the rest.
+// RGG adjacency is symmetric, so "i -> g_j is an edge of strip s" is answered from g_j's own list when s is remote.
+__global__ void __launch_bounds__(256) k_rande_keys(RandeParams rp, const long long *soff, const int *di, const int *dgj, long long nr,
+                                                    const long long *rowptr, const Edge16 *edges, unsigned long long *key,
+                                                    unsigned int *qidx) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nr; q += (long long)gridDim.x * blockDim.x) {
+    const int s = rande_stream_of(soff, rp.p, q);
+    const long long i = di[q], gj = dgj[q];
+    const int target = (int)(gj / rp.n);
+    const long long j = gj - (long long)target * rp.n, gi = (long long)s * rp.n + i;
+    unsigned long long k = ~0ULL;
+    if ((s == rp.me || target == rp.me) && i != j) {
+      const long long lv = s == rp.me ? i : j, want = s == rp.me ? gj : gi;
+      long long lo = rowptr[lv], hi = rowptr[lv + 1];
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (edges[mid].tail < want) lo = mid + 1; else hi = mid;
+      }
+      const bool in_rgg = lo < rowptr[lv + 1] && edges[lo].tail == want;
+      if (!in_rgg) k = (unsigned long long)gi * (unsigned long long)rp.nv + (unsigned long long)gj;
+    }
+    key[q] = k;
+    qidx[q] = (unsigned int)q;
+  }
+}
+
+// after the stable sort by key: the first draw of every run of equal keys is the one the reference keeps
+__global__ void __launch_bounds__(256) k_rande_first(const unsigned long long *skey, const unsigned int *sq, long long nr, RandeParams rp,
+                                                     const long long *soff, const int *dgj, unsigned int *emit) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nr; k += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = skey[k];
+    const unsigned int q = sq[k];
+    unsigned int cnt = 0;
+    if (key != ~0ULL && (k == 0 || skey[k - 1] != key)) {
+      const int s = rande_stream_of(soff, rp.p, q);
+      const int target = (int)((long long)dgj[q] / rp.n);
+      cnt = (s == rp.me ? 1u : 0u) + (target == rp.me ? 1u : 0u);
+    }
+    emit[q] = cnt;
+  }
+}
+
+// the extra records of this strip in the reference's push order (stream, draw, forward before reverse):
+// xkey = (local source vertex, tail) for the stable sort that follows, xw = weight
+__global__ void __launch_bounds__(256) k_rande_emit(RandeParams rp, RggParams gp, const long long *soff, const int *di, const int *dgj,
+                                                    long long nr, const unsigned int *emit, const unsigned int *epos, int unit,
+                                                    const double *X3, const double *Y3, unsigned long long *xkey, double *xw,
+                                                    unsigned int *xidx, unsigned int *add) {
+  const int s0 = max(0, rp.me - 1);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nr; q += (long long)gridDim.x * blockDim.x) {
+    const unsigned int cnt = emit[q];
+    if (!cnt) continue;
+    const int s = rande_stream_of(soff, rp.p, q);
+    const long long i = di[q], gj = dgj[q];
+    const int target = (int)(gj / rp.n);
+    const long long j = gj - (long long)target * rp.n, gi = (long long)s * rp.n + i;
+    double w = 1.0;
+    if (!unit) {
+      if (target == s || target == s - 1 || target == s + 1) {
+        const double dx = __dsub_rn(X3[(long long)(s - s0) * rp.n + i], X3[(long long)(target - s0) * rp.n + j]);
+        const double dy = __dsub_rn(Y3[(long long)(s - s0) * rp.n + i], Y3[(long long)(target - s0) * rp.n + j]);
+        w = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      } else {
+        // minstd_rand0((unsigned)hash(g_i * nv + g_j)) -> uniform_real_distribution(0.01, 1.0)
+        unsigned long long x = (unsigned long long)(unsigned int)((unsigned long long)gi * (unsigned long long)rp.nv + (unsigned long long)gj) % 2147483647ULL;
+        if (x == 0) x = 1;
+        const unsigned long long o1 = mulmod31(x, 16807ULL), o2 = mulmod31(o1, 16807ULL);
+        w = __dadd_rn(__dmul_rn(canonical2(o1, o2, gp), __dsub_rn(1.0, 0.01)), 0.01);
+      }
+    }
+    unsigned int e = epos[q];
+    if (s == rp.me) {
+      xkey[e] = ((unsigned long long)i << 31) | (unsigned long long)gj;
+      xw[e] = w; xidx[e] = e;
+      atomicAdd(&add[i], 1u);
+      e++;
+    }
+    if (target == rp.me) {
+      xkey[e] = ((unsigned long long)j << 31) | (unsigned long long)gi;
+      xw[e] = w; xidx[e] = e;
+      atomicAdd(&add[j], 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_rande_rowptr(const long long *rowptr, const unsigned int *xstart, long long n, long long *nrow) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v <= n; v += (long long)gridDim.x * blockDim.x)
+    nrow[v] = rowptr[v] + (long long)xstart[v];
+}
+
+// per vertex: RGG list and extras (both ascending by tail) merged, RGG entries first among equal tails, extras in
+// push order among themselves (= std::stable_sort of the concatenation)
+__global__ void __launch_bounds__(256) k_rande_merge(const long long *rowptr, const Edge16 *edges, const unsigned int *xstart,
+                                                     const unsigned long long *sxkey, const unsigned int *sxidx, const double *xw,
+                                                     long long n, const long long *nrow, Edge16 *out) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    long long a = rowptr[v];
+    const long long ae = rowptr[v + 1];
+    unsigned int b = xstart[v];
+    const unsigned int be = xstart[v + 1];
+    Edge16 *o = out + nrow[v];
+    while (a < ae || b < be) {
+      bool take_a = b >= be;
+      long long bt = 0;
+      if (!take_a) {
+        bt = (long long)(sxkey[b] & 0x7fffffffULL);
+        take_a = a < ae && edges[a].tail <= bt;
+      }
+      if (take_a) *o++ = edges[a++];
+      else { Edge16 r; r.tail = bt; r.weight = xw[sxidx[b]]; *o++ = r; b++; }
+    }
+  }
+}
+
 }  // namespace mv

@@ -52,7 +52,7 @@ def lib():
         L.mvgpu_upload_shard.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.mvgpu_attach_shard_device.argtypes = [vp, i64, vp, i64, i64, vp, vp]
         L.mvgpu_generate_rgg_shard.argtypes = [vp, i64, ci, ctypes.POINTER(i64)]
-        L.mvgpu_generate_rgg_shard_ex.argtypes = [vp, i64, ci, ci, ctypes.POINTER(i64)]
+        L.mvgpu_generate_rgg_shard_ex.argtypes = [vp, i64, ci, ci, ctypes.c_double, ctypes.POINTER(i64)]
         L.mvgpu_download_shard.argtypes = [vp, vp, vp]
         L.mvgpu_louvain.argtypes = [vp, dbl, dbl, ctypes.POINTER(ci), ctypes.POINTER(dbl)]
         L.mvgpu_get_communities.argtypes = [vp, vp]
@@ -151,10 +151,12 @@ class LouvainGPU:
         self.lnv = int(lnv)
         self._keep = keepalive
 
-    def generate_rgg(self, nv_global, unit_weight=True, lcg=False):
-        """Build this rank's strip of `miniVite -n nv_global [-w] [-l]` on the device (reference GenerateRGG); returns lne."""
+    def generate_rgg(self, nv_global, unit_weight=True, lcg=False, random_edge_percent=0.0):
+        """Build this rank's strip of `miniVite -n nv_global [-w] [-l] [-p pct]` on the device (reference GenerateRGG);
+        returns lne.  With several ranks and random_edge_percent > 0 the call is collective (after comm_init)."""
         lne = ctypes.c_int64(0)
-        _ck(lib().mvgpu_generate_rgg_shard_ex(self._h, int(nv_global), int(bool(unit_weight)), int(bool(lcg)), ctypes.byref(lne)))
+        _ck(lib().mvgpu_generate_rgg_shard_ex(self._h, int(nv_global), int(bool(unit_weight)), int(bool(lcg)),
+                                              float(random_edge_percent), ctypes.byref(lne)))
         self.lnv = int(nv_global) // self.nranks
         self._lne = lne.value
         return lne.value

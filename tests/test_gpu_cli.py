@@ -74,3 +74,20 @@ def test_cli_ranks_sharing_one_device(golden):
         assert f"Number of edges: {case['ne']}" in p.stdout
         it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
         assert [(float(a[1]), int(a[2]), a[3]) for a in it] == [(float(g["modularity"]), g["moved"], g["chash"]) for g in case["trace"]], args
+
+
+def test_cli_device_generation_with_random_edges():
+    """-D -p: the random long edges are generated on the GPU too; report lines and trace equal the host-generated run
+    (single rank, and two ranks sharing device 0 where the generator sums the edge count over the ranks)."""
+    env = dict(os.environ, MVGPU_OPTIONS="host_transport=1")
+    for extra in ([], ["-g", "2"]):
+        outs = []
+        for dev in ([], ["-D"]):
+            p = subprocess.run([EXE, "-n", "32768", "-p", "10", "-T"] + extra + dev, capture_output=True, text=True, timeout=300, env=env)
+            assert p.returncode == 0, p.stderr[-2000:]
+            ne = re.search(r"Number of edges: (\d+)", p.stdout).group(1)
+            mod = re.search(r"Modularity, #Iterations: (\S+), (\d+)", p.stdout).groups()
+            it = re.findall(r"ITER (\d+) mod=(\S+) moved=(\d+) chash=([0-9a-f]+)", p.stderr)
+            assert len(it) == int(mod[1])
+            outs.append((ne, mod, it))
+        assert outs[0] == outs[1], extra
